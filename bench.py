@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py — GoldDragon 1920x1080, 500 spp, 5 bounces (BASELINE.json configs[1]) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+    python bench.py --impl reference ...                    # the reference's algorithm on the host cores (the oracle port)
+
+A step = one pass of the hot path over one frame: W*H*spp paths through camera ray generation,
+Scene::intersect (sphere / planes / uniform-grid DDA), the BRDF bounce loop and the tile accumulator.
+Metric: Msamples/s (paths per second, whole job).  The dragon mesh is missing from the reference
+snapshot, so the scene uses the documented STAND-IN mesh (raymond_b200.fixtures.dragon_standin).
+
+N > 1 (torchrun, one rank per GPU): weak scaling — every rank renders `spp` samples per pixel of the
+same frame (global sample indices interleaved, rank g takes g, g+N, ...), then the per-rank f64
+accumulators are summed onto rank 0 with an NCCL reduce inside the timed region.
+
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+METRIC = "Msamples/sec (paths x 5 bounces), GoldDragon 1920x1080 500 spp"
+UNIT = "Msamples/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=3)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--width", type=int, default=1920)
+    p.add_argument("--height", type=int, default=1080)
+    p.add_argument("--spp", type=int, default=500)
+    p.add_argument("--bounces", type=int, default=5)
+    p.add_argument("--scene", default="gold_dragon", choices=["gold_dragon", "reflective_spheres", "reflective_spheres_dof"])
+    p.add_argument("--seed", type=int, default=2026)
+    p.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline sample")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+def scene_objects(name):
+    from raymond_b200 import fixtures as F
+    if name == "gold_dragon":
+        return F.gold_dragon(F.dragon_standin()), "GoldDragon (STAND-IN mesh, 871200 triangles; dragon_vrip.ply is missing from the reference snapshot)"
+    if name == "reflective_spheres":
+        return F.reflective_spheres(), "ReflectiveSpheres"
+    return F.reflective_spheres(), "ReflectiveSpheres + aperture sampling (focal 2.5, radius 0.5)"
+
+
+def camera_for(args):
+    from raymond_b200 import fixtures as F
+    if args.scene == "reflective_spheres_dof":
+        return F.camera(args.width, args.height, focal_length=2.5, aperture_radius=0.5)
+    return F.camera(args.width, args.height)
+
+
+# ------------------------------------------------------------------------------- clocks
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons every 200 ms during the timed region (NVML)."""
+
+    def __init__(self, device_index: int):
+        super().__init__(daemon=True)
+        self.idx = device_index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[device_index]) if vis and vis.split(",")[device_index].isdigit() else device_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            log(f"[bench] NVML unavailable: {e}")
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop_evt.wait(0.2)
+
+    def finish(self) -> dict:
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------- CPU arm (oracle port)
+
+def oracle_scene(objs):
+    from oracle import oracle as O
+    s = O.Scene()
+    for o in objs:
+        if o[0] == "sphere":
+            s.add_sphere(o[1], o[2], o[3])
+        elif o[0] == "plane":
+            s.add_plane(o[1], o[2], o[3])
+        else:
+            s.add_grid(O.AccGrid.build_from_mesh(O.Mesh.from_triangles(o[1])), o[2])
+    return s
+
+
+def cpu_sample_plan(sc, cam, bounces, target_s, cores):
+    """Pick a bounded sample (full frame, k spp) worth about `target_s` seconds of CPU work."""
+    from oracle import oracle as O
+    small = dict(cam, width=max(cam["width"] // 4, 16), height=max(cam["height"] // 4, 16))
+    O.render(sc, small, 1, seed=1, bounce_limit=bounces, worker_count=cores)          # page-in / warm caches
+    t0 = time.perf_counter()
+    O.render(sc, small, 1, seed=2, bounce_limit=bounces, worker_count=cores)
+    rate = small["width"] * small["height"] / (time.perf_counter() - t0)
+    frame = cam["width"] * cam["height"]
+    spp = int(max(1, min(64, round(rate * target_s / frame))))
+    return spp, rate
+
+
+def run_cpu(sc, cam, spp, bounces, cores, seed):
+    from oracle import oracle as O
+    t0 = time.perf_counter()
+    _, cnt = O.render(sc, cam, spp, seed=seed, bounce_limit=bounces, worker_count=cores)
+    dt = time.perf_counter() - t0
+    return cnt["samples"] / dt / 1e6, dt, cnt
+
+
+def bench_reference(args):
+    """The reference's own algorithm on the host cores: the C++ oracle port (no rustc here, so the reference
+    itself cannot be built), reference threading model (worker threads over a FIFO tile queue, 1 spp per pass)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    objs, label = scene_objects(args.scene)
+    cam = camera_for(args)
+    sc = oracle_scene(objs)
+    per_step_target = max(2.0, min(20.0, 150.0 / max(args.steps + args.warmup, 1)))
+    spp, _ = cpu_sample_plan(sc, cam, args.bounces, per_step_target, cores)
+    for i in range(args.warmup):
+        run_cpu(sc, cam, spp, args.bounces, cores, args.seed + i)
+    t0 = time.perf_counter()
+    n = 0
+    for i in range(args.steps):
+        _, _, cnt = run_cpu(sc, cam, spp, args.bounces, cores, args.seed + 100 + i)
+        n += cnt["samples"]
+    dt = time.perf_counter() - t0
+    value = n / dt / 1e6
+    sample = f"{cam['width']}x{cam['height']} x {spp} spp per step (full frame, reduced spp; the rate is spp-invariant)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": f"{label} {args.width}x{args.height}, {args.spp} spp, {args.bounces} bounces",
+                                        "scene": args.scene, "spp": args.spp, "bounces": args.bounces, "tile": [32, 32]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------- GPU arm
+
+def bench_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from raymond_b200 import api as A
+    from raymond_b200 import build as B
+    from raymond_b200 import distributed as D
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this implementation has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    B.build()
+
+    objs, label = scene_objects(args.scene)
+    cam = camera_for(args)
+    W, H, spp = args.width, args.height, args.spp
+    t0 = time.perf_counter()
+    scene = A.Scene.from_fixture(objs)                   # host side: Mesh::new + AccGrid::build_from_mesh
+    host_build_s = time.perf_counter() - t0
+    settings = A.Settings(A.CameraSettings.from_fixture(cam), spp * world, (32, 32), args.bounces)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # ---- resident-scene throughput (`value`): scene in HBM, accumulator in HBM, NCCL reduce included
+    dr = D.DistributedRenderer(scene, settings, device=local, seed=args.seed, flags=A.FLAG_STAGE_TIMING)
+    total_spp = spp * world                               # weak scaling: per-GPU work fixed
+    for _ in range(args.warmup):
+        dr.clear()
+        dr.render(total_spp)
+    dr.synchronize()
+    s0 = dr.stats()
+    st0 = dr.renderer.stage_stats()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(dr.stream)
+    for _ in range(args.steps):
+        dr.clear()
+        dr.render(total_spp)
+    ev1.record(dr.stream)
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.finish()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    s1 = dr.stats()
+    st1 = dr.renderer.stage_stats()
+    samples_total = W * H * total_spp * args.steps
+    value = samples_total / ms_total / 1e3
+    launches = int(s1["kernel_launches"] - s0["kernel_launches"])
+    rays = int(s1["rays"] - s0["rays"])
+    frame = dr.frame(total_spp)
+    mean_radiance = [float(x) for x in frame.mean(axis=(0, 1))] if frame is not None else None
+
+    # ---- roofline of the dominant kernel (rank 0): live CUDA-event time per stage over the timed region,
+    #      algorithmic bytes from an instrumented pass of the same rays (C cells visited, T triangle tests)
+    roofline = None
+    stages = None
+    if rank == 0:
+        stage_ms = [b - a for a, b in zip(st0["ms"], st1["ms"])]
+        stage_launch = [b - a for a, b in zip(st0["launches"], st1["launches"])]
+        stage_rays = [b - a for a, b in zip(st0["rays"], st1["rays"])]
+        counted = A.Renderer(scene, A.Settings(settings.camera_settings, 4, (32, 32), args.bounces),
+                             A.GpuOptions(device=local, seed=args.seed, flags=A.FLAG_COUNT_WORK, batch_spp=4))
+        counted.render(0, 4)
+        cs = counted.stage_stats()
+        counted.close()
+        top = int(np.argmax(stage_ms))
+        stages = []
+        for d in range(0, args.bounces + 1):
+            if stage_launch[d] == 0:
+                continue
+            if d == 0:
+                # accumulator: read 24 B per path + read/write 48 B per pixel per batch
+                bytes_total = 24.0 * samples_total / world + 48.0 * W * H * stage_launch[0]
+                per_ray = None
+            else:
+                r_ = max(cs["rays"][d], 1)
+                C_, T_, S_ = cs["cells"][d] / r_, cs["triangle_tests"][d] / r_, cs["shaded_triangles"][d] / r_
+                per_ray = 64.0 + 8.0 * C_ + 76.0 * T_ + 72.0 * S_        # SURVEY §8d bytes-per-ray model
+                bytes_total = per_ray * stage_rays[d]
+            stages.append({"stage": "accumulate" if d == 0 else f"bounce depth {d}", "ms": stage_ms[d], "launches": stage_launch[d],
+                           "rays": stage_rays[d], "alg_bytes_per_ray": per_ray,
+                           "achieved_gbs": bytes_total / (stage_ms[d] * 1e-3) / 1e9 if stage_ms[d] > 0 else None,
+                           "share": stage_ms[d] / max(sum(stage_ms), 1e-9)})
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        topst = next(s for s in stages if s["stage"] == ("accumulate" if top == 0 else f"bounce depth {top}"))
+        ach = topst["achieved_gbs"]
+        roofline = {"bound": "hbm", "kernel": "k_accumulate" if top == 0 else ("k_bounce<first>" if top == 1 else "k_bounce"),
+                    "stage": topst["stage"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if ach else None, "traffic": None,
+                    "peak_source": peak_src, "alg_bytes_per_ray": topst["alg_bytes_per_ray"], "launch_ms_avg": topst["ms"] / max(topst["launches"], 1),
+                    "share_of_step": topst["share"],
+                    "note": "f64 no-FMA traversal: latency/issue bound, not HBM bound — see DESIGN.md; traffic from ncu in profiles/"}
+    dr.close()
+    del dr
+
+    # ---- end to end through the reference-facing call: render_tiled(scene, settings) -> await(), host buffers:
+    #      scene flatten + H2D inside, D2H of the f64 accumulator + tile slicing + averaging inside
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(1, args.steps)
+        times, h2d, d2h = [], 0, W * H * 24
+        for i in range(1 + e2e_steps):
+            barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if world == 1:
+                task = A.render_tiled(scene, settings, A.GpuOptions(device=local, seed=args.seed + i))
+                out = task.await_()
+                stt = task.stats()
+                del task
+            else:
+                dre = D.DistributedRenderer(scene, settings, device=local, seed=args.seed + i)
+                dre.render(total_spp)
+                out = dre.frame(total_spp)
+                stt = dre.stats()
+                dre.close()
+            torch.cuda.synchronize()
+            barrier()
+            dt = time.perf_counter() - t0
+            h2d = int(stt["upload_bytes"])
+            if i > 0:
+                times.append(dt)
+        tt = torch.tensor([sum(times)], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": W * H * total_spp * e2e_steps / float(tt.item()) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": 1e3 * float(tt.item()) / e2e_steps,
+               "call": "render_tiled(scene, settings).await()" if world == 1 else "DistributedRenderer(create+render+reduce+frame)"}
+
+    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        osc = oracle_scene(objs)
+        cspp, _ = cpu_sample_plan(osc, cam, args.bounces, args.cpu_seconds, cores)
+        v, dt, cnt = run_cpu(osc, cam, cspp, args.bounces, cores, args.seed)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{W}x{H} x {cspp} spp of the same scene ({dt:.1f} s; reference threading model, f64, -ffp-contract=off)",
+               "rays_per_path": cnt["rays"] / max(cnt["samples"], 1)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{label} {W}x{H}, {spp} spp per GPU ({total_spp} total), {args.bounces} bounces", "scene": args.scene,
+                       "spp_per_gpu": spp, "bounces": args.bounces, "tile": [32, 32], "parallelism": f"sample-split x{world} + ncclReduce(sum)",
+                       "l2": "inputs exceed L2 (scene ~180 MB + 1.4 GB of wavefront queues per batch); no explicit flush",
+                       "mesh": "stand-in" if args.scene == "gold_dragon" else "analytic"},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "mrays_per_s": rays * world / ms_total / 1e3 if world == 1 else None, "rays_per_path": rays / max(samples_total / world, 1),
+            "stages": stages, "host_grid_build_s": host_build_s, "mean_radiance": mean_radiance,
+            "nonfinite_samples": int(s1["nonfinite_samples"]),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        bench_reference(args)
+    else:
+        bench_ours(args)
+
+
+if __name__ == "__main__":
+    main()

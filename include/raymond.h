@@ -192,6 +192,8 @@ typedef enum rm_partition {
 } rm_partition;
 
 #define RM_FLAG_KEEP_NONFINITE 1u  /* accumulate NaN/Inf samples like the reference instead of dropping+counting them */
+#define RM_FLAG_STAGE_TIMING 2u    /* bracket every kernel launch with CUDA events; totals per wavefront stage in rm_stage_stats */
+#define RM_FLAG_COUNT_WORK 4u      /* instrumented kernels: count grid cells visited and triangle tests per stage (slower) */
 
 /* GPU-side knobs that have no counterpart in the reference. Zero-initialise
  * for defaults (device 0, one rank, library-owned stream and buffers). */
@@ -255,6 +257,7 @@ typedef struct rm_stats {
     uint64_t kernel_launches;    /* launches of this library's kernels */
     double device_ms;            /* CUDA-event time of the render section */
     double upload_ms;            /* host flatten + H2D of the scene */
+    uint64_t upload_bytes;       /* bytes copied host -> device for the scene and the pixel map */
 } rm_stats;
 int rm_task_stats(rm_task* task, rm_stats* out);
 void rm_task_destroy(rm_task* task);
@@ -285,13 +288,29 @@ rm_renderer* rm_renderer_create_on(rm_device_scene* ds, const rm_settings* setti
 int rm_renderer_render(rm_renderer* r, size_t first_sample, size_t count, size_t stride);
 /* Device pointer of the W*H rm_vec3 running sums. */
 void* rm_renderer_accum_device(rm_renderer* r);
-int rm_renderer_clear(rm_renderer* r);
+int rm_renderer_clear(rm_renderer* r);   /* zero the running sums (statistics stay cumulative) */
 int rm_renderer_sync(rm_renderer* r);
 /* D2H of the running sums (no division). */
 int rm_renderer_read_sums(rm_renderer* r, rm_vec3* out_host);
 /* D2H of sum / sample_count, row-major W*H. */
 int rm_renderer_read_frame(rm_renderer* r, size_t sample_count, rm_vec3* out_host);
 int rm_renderer_stats(rm_renderer* r, rm_stats* out);
+
+/* Per-stage breakdown.  Slot d (1 <= d < RM_STAGE_SLOTS-1) is the wavefront stage that traces and
+ * shades the rays of depth d (deeper stages share the last such slot); slot 0 is the accumulator
+ * kernel.  `ms`/`launches` need RM_FLAG_STAGE_TIMING, `cells`/`triangle_tests`/`shaded_triangles`
+ * need RM_FLAG_COUNT_WORK; `rays` is always counted.  These are the C and T of the algorithmic
+ * bytes-per-ray model (64 + 8 C + 76 T + 72 per shaded triangle hit). */
+#define RM_STAGE_SLOTS 16
+typedef struct rm_stage_stats {
+    double ms[RM_STAGE_SLOTS];
+    uint64_t launches[RM_STAGE_SLOTS];
+    uint64_t rays[RM_STAGE_SLOTS];
+    uint64_t cells[RM_STAGE_SLOTS];
+    uint64_t triangle_tests[RM_STAGE_SLOTS];
+    uint64_t shaded_triangles[RM_STAGE_SLOTS];
+} rm_stage_stats;
+int rm_renderer_stage_stats(rm_renderer* r, rm_stage_stats* out);
 void rm_renderer_destroy(rm_renderer* r);
 
 /* Tile rectangles in the reference's queue order (column-major: y advances

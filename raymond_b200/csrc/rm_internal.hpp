@@ -1,0 +1,63 @@
+// rm_internal.hpp — host-side object model behind include/raymond.h (not part of the ABI).
+#pragma once
+
+#include <atomic>
+#include <condition_variable>
+#include <cstdint>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/raymond.h"
+
+namespace rm {
+
+void set_error(const std::string& msg);
+int fail(int status, const std::string& msg);
+
+// Mesh { triangles, bounding_box }                         reference core/src/geometry/mesh.rs:10-13
+struct Mesh {
+    std::vector<rm_triangle> triangles;
+    rm_aabb bounds;
+};
+rm_aabb mesh_bounds(const rm_triangle* tris, size_t n);    // Mesh::find_mesh_bounds  mesh.rs:123-140
+
+// AccGrid in compressed-row form.  The reference keeps `cells` (offset into
+// `mapping_table`) and `mapping_table` ([count, tri...] per cell, acc_grid.rs:67-74);
+// here the same per-cell lists, in the same ascending-triangle order, are stored
+// as cell_start[c]..cell_start[c+1] into `references`.
+struct Grid {
+    std::vector<rm_triangle> triangles;
+    rm_aabb bounds;
+    uint64_t resolution[3];
+    rm_vec3 cell_size;
+    std::vector<uint32_t> cell_start;   // n_cells + 1
+    std::vector<uint32_t> references;   // triangle indices
+    uint64_t n_cells() const { return resolution[0] * resolution[1] * resolution[2]; }
+};
+// AccGrid::build_from_mesh                                 acc_grid.rs:36-83
+int build_grid(std::vector<rm_triangle>&& tris, const rm_aabb& bounds, std::shared_ptr<Grid>* out);
+
+enum GeometryKind : int { GEOM_PLANE = 0, GEOM_SPHERE = 1, GEOM_GRID = 2 };   // scene.rs:9-13
+
+struct Object {                                             // scene.rs:33-37
+    int geometry;
+    rm_vec3 origin;
+    rm_vec3 normal;
+    double radius;
+    std::shared_ptr<Grid> grid;
+    rm_material material;
+};
+
+struct TileRect { size_t left, top, width, height; };
+// tile split of render_tiled                               src/trace.rs:142-173
+std::vector<TileRect> tile_layout(size_t W, size_t H, size_t tw, size_t th);
+
+}  // namespace rm
+
+struct rm_mesh { rm::Mesh mesh; };
+struct rm_grid { std::shared_ptr<rm::Grid> grid; std::atomic<int> refs{1}; };
+struct rm_scene { std::vector<rm::Object> objects; };

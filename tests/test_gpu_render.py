@@ -1,0 +1,195 @@
+"""GPU parity, statistical scope: the wavefront path tracer through the C ABI vs the oracle's render_tiled.
+
+Both sides draw the reference's rand::random::<f64>() calls from the same counter-based stream
+(Philox4x32-10 keyed by seed; pixel, sample, depth, draw), so the comparison can be far tighter than
+north_star (b) asks for: apart from rare paths where a last-ulp libm difference (CUDA sincos vs glibc)
+flips a branch, every pixel sum agrees to ~1e-12.  The noise-floor test of SURVEY §8d (RMSE against an
+independent-seed oracle render, mean luminance) is applied as well, with the tolerances written below."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from raymond_b200 import api as A
+from raymond_b200 import fixtures as F
+
+from util import oracle_scene, product_scene, settings
+
+pytestmark = pytest.mark.gpu
+
+LUMA = np.array([0.2126, 0.7152, 0.0722])
+
+
+def gpu_render(objs, cam, spp, seed=0, **kw):
+    opts = A.GpuOptions(seed=seed, **{k: v for k, v in kw.items() if k in ("rank", "world_size", "partition", "batch_spp", "flags")})
+    st = settings(cam, spp, bounce_limit=kw.get("bounce_limit", 5))
+    r = A.Renderer(product_scene(objs), st, opts)
+    r.render(kw.get("first", 0), kw.get("count", spp), kw.get("stride", 1))
+    sums = r.read_sums()
+    stats = r.stats()
+    r.close()
+    return sums, stats
+
+
+def compare_same_stream(gpu_sums, ora_sums, spp, what, max_outlier_frac=0.004):
+    g, o = gpu_sums / spp, ora_sums / spp
+    assert np.isfinite(g).all()
+    diff = np.abs(g - o).max(axis=-1)
+    scale = np.maximum(np.abs(o).max(axis=-1), 1e-3)
+    outliers = (diff / scale) > 1e-9
+    frac = outliers.mean()
+    assert frac <= max_outlier_frac, f"{what}: {frac:.4%} of pixels differ beyond 1e-9 relative (allowed {max_outlier_frac:.2%})"
+    # clamp like SURVEY §8d (linear radiance clamped to [0, 10]) so one firefly cannot dominate
+    gc, oc = np.clip(g, 0, 10), np.clip(o, 0, 10)
+    mean_l_g, mean_l_o = (gc @ LUMA).mean(), (oc @ LUMA).mean()
+    assert abs(mean_l_g - mean_l_o) <= 0.005 * mean_l_o, f"{what}: mean luminance {mean_l_g} vs {mean_l_o}"
+    return frac
+
+
+def test_reflective_spheres_same_stream():
+    objs, cam, spp = F.reflective_spheres(), F.camera(160, 120), 8
+    g, gs = gpu_render(objs, cam, spp, seed=3)
+    o, oc = O.render(oracle_scene(objs), cam, spp, seed=3)
+    frac = compare_same_stream(g, o, spp, "ReflectiveSpheres 160x120x8")
+    assert gs["samples"] == oc["samples"] == 160 * 120 * spp
+    assert gs["nonfinite_samples"] == oc["nonfinite"]
+    # the GPU stops a path whose throughput became exactly zero; the oracle keeps tracing it
+    assert gs["rays"] <= oc["rays"]
+    assert gs["rays"] > 0.5 * oc["rays"]
+
+
+def test_reflective_spheres_noise_floor():
+    """RMSE(GPU, oracle seed A) <= 1.15 RMSE(oracle seed B, oracle seed A) per channel, different streams."""
+    objs, cam, spp = F.reflective_spheres(), F.camera(128, 96), 32
+    sc = oracle_scene(objs)
+    a, _ = O.render(sc, cam, spp, seed=11)
+    b, _ = O.render(sc, cam, spp, seed=12)
+    g, _ = gpu_render(objs, cam, spp, seed=13)
+    clip = lambda x: np.clip(x / spp, 0, 10)
+    rmse0 = np.sqrt(((clip(a) - clip(b)) ** 2).mean(axis=(0, 1)))
+    rmse = np.sqrt(((clip(g) - clip(a)) ** 2).mean(axis=(0, 1)))
+    assert (rmse <= 1.15 * rmse0).all(), f"rmse {rmse} vs floor {rmse0}"
+    la, lg = (clip(a) @ LUMA), (clip(g) @ LUMA)
+    se = np.sqrt(la.var() / la.size + lg.var() / lg.size)
+    assert abs(la.mean() - lg.mean()) <= max(0.005 * la.mean(), 3 * se)
+    # tonemapped 8-bit view (cli_old/src/main.rs:157-181)
+    ta, tg = F.tonemap(a / spp).astype(float), F.tonemap(g / spp).astype(float)
+    tb = F.tonemap(b / spp).astype(float)
+    assert np.sqrt(((tg - ta) ** 2).mean()) <= 1.15 * np.sqrt(((tb - ta) ** 2).mean())
+
+
+def test_gold_dragon_same_stream():
+    objs, cam, spp = F.gold_dragon(F.dragon_standin(240, 60)), F.camera(160, 90), 4
+    g, gs = gpu_render(objs, cam, spp, seed=5)
+    o, oc = O.render(oracle_scene(objs), cam, spp, seed=5)
+    compare_same_stream(g, o, spp, "GoldDragon stand-in 160x90x4", max_outlier_frac=0.01)
+    assert gs["nonfinite_samples"] == oc["nonfinite"]
+
+
+def test_depth_of_field_same_stream():
+    """generate_primary_ray_with_dof (src/trace.rs:335-360), selected iff aperture_radius > 0."""
+    objs, spp = F.reflective_spheres(), 4
+    cam = F.camera(120, 80, focal_length=2.5, aperture_radius=0.5)
+    g, _ = gpu_render(objs, cam, spp, seed=9)
+    o, _ = O.render(oracle_scene(objs), cam, spp, seed=9)
+    compare_same_stream(g, o, spp, "DoF 120x80x4")
+    sharp, _ = gpu_render(objs, F.camera(120, 80), spp, seed=9)
+    assert np.abs(sharp - g).mean() > 1e-3       # the aperture actually changes the image
+
+
+@pytest.mark.parametrize("limit", [0, 1, 2, 5])
+def test_bounce_limits(limit):
+    objs, cam, spp = F.reflective_spheres(), F.camera(64, 48), 2
+    g, gs = gpu_render(objs, cam, spp, seed=1, bounce_limit=limit)
+    o, oc = O.render(oracle_scene(objs), cam, spp, seed=1, bounce_limit=limit)
+    if limit == 0:
+        assert not g.any() and not o.any()
+    else:
+        compare_same_stream(g, o, spp, f"bounce_limit {limit}", max_outlier_frac=0.01)
+    if limit == 1:
+        # only directly visible emitters contribute: ceiling pixels are exactly the emission
+        assert np.array_equal(g, o)
+
+
+def test_batching_is_invisible():
+    """Sums do not depend on how samples are batched into wavefronts (fixed summation order)."""
+    objs, cam, spp = F.reflective_spheres(), F.camera(96, 64), 6
+    a, _ = gpu_render(objs, cam, spp, seed=2, batch_spp=1)
+    b, _ = gpu_render(objs, cam, spp, seed=2, batch_spp=4)
+    c, _ = gpu_render(objs, cam, spp, seed=2)
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+
+
+def test_sample_partition_is_additive():
+    """rank g of G renders global samples g, g+G, ...; the per-rank sums add up to the 1-GPU image (FP association aside)."""
+    objs, cam, spp = F.reflective_spheres(), F.camera(96, 64), 8
+    full, _ = gpu_render(objs, cam, spp, seed=4)
+    parts = [gpu_render(objs, cam, spp, seed=4, first=g, count=spp // 2, stride=2)[0] for g in range(2)]
+    assert np.allclose(parts[0] + parts[1], full, rtol=1e-12, atol=1e-12)
+    o0, _ = O.render(oracle_scene(objs), cam, spp // 2, seed=4, first_sample=1, sample_stride=2)
+    assert np.abs(parts[1] / 4 - o0 / 4).max(axis=-1).mean() < 1e-6
+
+
+def test_tile_partition_is_disjoint():
+    """Tiles dealt round-robin in the reference's queue order; each rank's frame is zero outside its tiles."""
+    objs, cam, spp = F.reflective_spheres(), F.camera(100, 70), 3
+    full, _ = gpu_render(objs, cam, spp, seed=6)
+    parts = [gpu_render(objs, cam, spp, seed=6, rank=g, world_size=3, partition=A.PARTITION_TILES)[0] for g in range(3)]
+    assert np.array_equal(parts[0] + parts[1] + parts[2], full)
+    owner = np.zeros((70, 100), dtype=int) - 1
+    for i, (l, t, w, h) in enumerate(A.tile_layout(settings(cam, spp))):
+        owner[t:t + h, l:l + w] = i % 3
+    for g in range(3):
+        assert not parts[g][owner != g].any()
+        assert np.array_equal(parts[g][owner == g], full[owner == g])
+
+
+def test_render_tiled_task_handle():
+    """render_tiled / poll / await (src/trace.rs:82-230): message kinds, tile rectangles, running sums, averaged frame."""
+    objs, cam, spp = F.reflective_spheres(), F.camera(100, 70), 6
+    st = settings(cam, spp, tile=(32, 32), spi=2)
+    task = A.render_tiled(product_scene(objs), st, A.GpuOptions(seed=8))
+    stats = task.stats()          # blocks until the driver thread is done
+    assert task.finished()
+    msgs = []
+    while True:
+        m = task.poll()
+        if m is None:
+            break
+        msgs.append(m)
+    layout = A.tile_layout(st)
+    assert len(layout) == 4 * 3
+    progressed = [m for m in msgs if m.kind == "TileProgressed"]
+    finished = [m for m in msgs if m.kind == "TileFinished"]
+    assert len(finished) == len(layout) and len(progressed) == 2 * len(layout)      # after 2 and 4 of 6 samples
+    assert sorted({m.tile.sample_count for m in progressed}) == [2, 4]
+    assert [(m.tile.left, m.tile.top, m.tile.width, m.tile.height) for m in finished] == [tuple(r) for r in layout]
+    ref, _ = gpu_render(objs, cam, spp, seed=8)
+    for m in finished:
+        t = m.tile
+        assert t.sample_count == spp
+        assert np.array_equal(t.data, ref[t.top:t.top + t.height, t.left:t.left + t.width])
+    assert stats["samples"] == 100 * 70 * spp and stats["kernel_launches"] > 0
+    # await(): tile.data / sample_count, row-major W*H; TileProgressed messages are skipped
+    task2 = A.render_tiled(product_scene(objs), st, A.GpuOptions(seed=8))
+    frame = task2.await_()
+    assert np.array_equal(frame, ref / spp)
+
+
+def test_callback_delivery():
+    objs, cam = F.reflective_spheres(), F.camera(64, 64)
+    st = settings(cam, 4, tile=(32, 32), spi=1)
+    task = A.render_tiled(product_scene(objs), st, A.GpuOptions(seed=1))
+    task.stats()
+    seen = []
+    task.set_callback(lambda tile: seen.append((tile.left, tile.top, tile.sample_count)))
+    n = task.async_await()
+    assert n == len(seen) == 12         # 3 progress rounds x 4 tiles; stops at the first TileFinished
+    assert sorted({s[2] for s in seen}) == [1, 2, 3]
+
+
+def test_missing_device_is_an_error_not_a_fallback():
+    sc = product_scene(F.reflective_spheres())
+    with pytest.raises(A.RaymondError):
+        sc.intersect(np.array([[0, 0, 0, 0, 0, 1.0]]), device=99)
+    with pytest.raises(A.RaymondError):
+        A.Renderer(sc, settings(F.camera(8, 8), 1), A.GpuOptions(device=99))
