@@ -31,6 +31,8 @@ import numpy as np
 
 METRIC = "Msamples/sec (paths x 5 bounces), GoldDragon 1920x1080 500 spp"
 UNIT = "Msamples/s"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, from the ncu --set full capture in profiles/ (None = not captured)
+NCU_TRAFFIC = {}
 
 
 def log(*a):
@@ -263,37 +265,53 @@ def bench_ours(args):
     frame = dr.frame(total_spp)
     mean_radiance = [float(x) for x in frame.mean(axis=(0, 1))] if frame is not None else None
 
-    # ---- roofline of the dominant kernel (rank 0): live CUDA-event time per stage over the timed region,
+    # ---- roofline of the dominant kernel (rank 0): live CUDA-event time per (kernel, depth) over the timed region,
     #      algorithmic bytes from an instrumented pass of the same rays (C cells visited, T triangle tests)
     roofline = None
     stages = None
     if rank == 0:
-        stage_ms = [b - a for a, b in zip(st0["ms"], st1["ms"])]
-        stage_launch = [b - a for a, b in zip(st0["launches"], st1["launches"])]
-        stage_rays = [b - a for a, b in zip(st0["rays"], st1["rays"])]
+        kinds = A.KERNEL_KINDS
+        d_ms = {k: [b - a for a, b in zip(st0["ms"][k], st1["ms"][k])] for k in kinds}
+        d_launch = {k: [b - a for a, b in zip(st0["launches"][k], st1["launches"][k])] for k in kinds}
+        d_rays = [b - a for a, b in zip(st0["rays"], st1["rays"])]
+        d_grid = [b - a for a, b in zip(st0["grid_rays"], st1["grid_rays"])]
+        d_shtri = [b - a for a, b in zip(st0["shaded_triangles"], st1["shaded_triangles"])]
         counted = A.Renderer(scene, A.Settings(settings.camera_settings, 4, (32, 32), args.bounces),
                              A.GpuOptions(device=local, seed=args.seed, flags=A.FLAG_COUNT_WORK, batch_spp=4))
         counted.render(0, 4)
         cs = counted.stage_stats()
         counted.close()
-        top = int(np.argmax(stage_ms))
-        stages = []
-        for d in range(0, args.bounces + 1):
-            if stage_launch[d] == 0:
-                continue
-            if d == 0:
-                # accumulator: read 24 B per path + read/write 48 B per pixel per batch
-                bytes_total = 24.0 * samples_total / world + 48.0 * W * H * stage_launch[0]
-                per_ray = None
-            else:
-                r_ = max(cs["rays"][d], 1)
-                C_, T_, S_ = cs["cells"][d] / r_, cs["triangle_tests"][d] / r_, cs["shaded_triangles"][d] / r_
-                per_ray = 64.0 + 8.0 * C_ + 76.0 * T_ + 72.0 * S_        # SURVEY §8d bytes-per-ray model
-                bytes_total = per_ray * stage_rays[d]
-            stages.append({"stage": "accumulate" if d == 0 else f"bounce depth {d}", "ms": stage_ms[d], "launches": stage_launch[d],
-                           "rays": stage_rays[d], "alg_bytes_per_ray": per_ray,
-                           "achieved_gbs": bytes_total / (stage_ms[d] * 1e-3) / 1e9 if stage_ms[d] > 0 else None,
-                           "share": stage_ms[d] / max(sum(stage_ms), 1e-9)})
+        total_ms = sum(sum(v) for v in d_ms.values())
+        stages, per_kernel = [], {}
+        for d in range(0, A.STAGE_SLOTS):
+            for k in kinds:
+                if d_launch[k][d] == 0:
+                    continue
+                C_ = T_ = None
+                if k == "accumulate":
+                    # reads 24 B per path, reads + writes 24 B per pixel per batch
+                    units, per_unit = samples_total / world, 24.0 + 48.0 * W * H * d_launch[k][d] / max(samples_total / world, 1)
+                elif k == "setup":
+                    # ray in (48 B; depth 1 generates it and writes it instead) + hit record out (16 B) + a 128-B traversal record per grid ray
+                    units = d_rays[d]
+                    per_unit = 48.0 + 16.0 + 128.0 * d_grid[d] / max(d_rays[d], 1)
+                elif k == "traverse":
+                    # B(ray) = 64 + 8 C + 76 T  (48-B ray in, 16-B hit out, 8 B per visited cell, 4 + 72 B per triangle test)
+                    g_ = max(cs["grid_rays"][d], 1)
+                    C_, T_ = cs["cells"][d] / g_, cs["triangle_tests"][d] / g_
+                    units, per_unit = d_grid[d], 64.0 + 8.0 * C_ + 76.0 * T_
+                else:
+                    # shade: ray + throughput + id + hit in (92 B), next ray out (76 B) or radiance out (24 B); +144 B (positions, normals) per shaded triangle
+                    units = d_rays[d]
+                    cont = d_rays[d + 1] if d + 1 < A.STAGE_SLOTS and d < args.bounces else 0
+                    per_unit = 92.0 + (76.0 * cont + 24.0 * (d_rays[d] - cont) + 144.0 * d_shtri[d]) / max(d_rays[d], 1)
+                bytes_total = per_unit * units
+                ms_ = d_ms[k][d]
+                stages.append({"kernel": "k_" + k, "depth": d, "ms": ms_, "launches": d_launch[k][d], "units": units,
+                               "alg_bytes_per_unit": per_unit, "cells_per_ray": C_, "tests_per_ray": T_,
+                               "achieved_gbs": bytes_total / (ms_ * 1e-3) / 1e9 if ms_ > 0 else None, "share": ms_ / max(total_ms, 1e-9)})
+                pk = per_kernel.setdefault(k, {"ms": 0.0, "launches": 0, "bytes": 0.0, "units": 0})
+                pk["ms"] += ms_; pk["launches"] += d_launch[k][d]; pk["bytes"] += bytes_total; pk["units"] += units
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -301,13 +319,17 @@ def bench_ours(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        topst = next(s for s in stages if s["stage"] == ("accumulate" if top == 0 else f"bounce depth {top}"))
-        ach = topst["achieved_gbs"]
-        roofline = {"bound": "hbm", "kernel": "k_accumulate" if top == 0 else ("k_bounce<first>" if top == 1 else "k_bounce"),
-                    "stage": topst["stage"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if ach else None, "traffic": None,
-                    "peak_source": peak_src, "alg_bytes_per_ray": topst["alg_bytes_per_ray"], "launch_ms_avg": topst["ms"] / max(topst["launches"], 1),
-                    "share_of_step": topst["share"],
-                    "note": "f64 no-FMA traversal: latency/issue bound, not HBM bound — see DESIGN.md; traffic from ncu in profiles/"}
+        top = max(per_kernel, key=lambda k: per_kernel[k]["ms"])
+        pk = per_kernel[top]
+        ach = pk["bytes"] / (pk["ms"] * 1e-3) / 1e9 if pk["ms"] > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": "k_" + top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": NCU_TRAFFIC.get("k_" + top), "peak_source": peak_src,
+                    "alg_bytes_per_launch": pk["bytes"] / max(pk["launches"], 1), "alg_bytes_per_unit": pk["bytes"] / max(pk["units"], 1),
+                    "unit_name": "grid ray" if top == "traverse" else ("path" if top == "accumulate" else "ray"),
+                    "launch_ms_avg": pk["ms"] / max(pk["launches"], 1), "launches": pk["launches"], "share_of_step": pk["ms"] / max(total_ms, 1e-9),
+                    "per_kernel_share": {"k_" + k: v["ms"] / max(total_ms, 1e-9) for k, v in per_kernel.items()},
+                    "note": "f64 no-FMA traversal of an L2-resident grid: bound by FP64 issue + L2 latency, not by HBM; "
+                            "see DESIGN.md and profiles/ for the ncu counters"}
     dr.close()
     del dr
 

@@ -296,16 +296,20 @@ int rm_renderer_read_sums(rm_renderer* r, rm_vec3* out_host);
 int rm_renderer_read_frame(rm_renderer* r, size_t sample_count, rm_vec3* out_host);
 int rm_renderer_stats(rm_renderer* r, rm_stats* out);
 
-/* Per-stage breakdown.  Slot d (1 <= d < RM_STAGE_SLOTS-1) is the wavefront stage that traces and
- * shades the rays of depth d (deeper stages share the last such slot); slot 0 is the accumulator
- * kernel.  `ms`/`launches` need RM_FLAG_STAGE_TIMING, `cells`/`triangle_tests`/`shaded_triangles`
- * need RM_FLAG_COUNT_WORK; `rays` is always counted.  These are the C and T of the algorithmic
- * bytes-per-ray model (64 + 8 C + 76 T + 72 per shaded triangle hit). */
+/* Per-stage breakdown of the wavefront.  Slot d (1 <= d < RM_STAGE_SLOTS) is the stage that traces
+ * and shades the rays of depth d (deeper stages share the last slot).  A stage is three kernels —
+ * kind 0 set-up (ray generation / analytic objects / grid entry), kind 1 grid traversal, kind 2
+ * shading — and kind 3, slot 0 is the accumulator kernel.  `ms` / `launches` need
+ * RM_FLAG_STAGE_TIMING; `cells` / `triangle_tests` need RM_FLAG_COUNT_WORK; the rest is always
+ * counted.  cells = C and triangle_tests = T of the algorithmic bytes-per-ray model
+ * (64 + 8 C + 76 T, + 72 per shaded triangle hit). */
 #define RM_STAGE_SLOTS 16
+#define RM_KERNEL_KINDS 4
 typedef struct rm_stage_stats {
-    double ms[RM_STAGE_SLOTS];
-    uint64_t launches[RM_STAGE_SLOTS];
-    uint64_t rays[RM_STAGE_SLOTS];
+    double ms[RM_KERNEL_KINDS][RM_STAGE_SLOTS];
+    uint64_t launches[RM_KERNEL_KINDS][RM_STAGE_SLOTS];
+    uint64_t rays[RM_STAGE_SLOTS];            /* Scene::intersect evaluations */
+    uint64_t grid_rays[RM_STAGE_SLOTS];       /* of those, rays that entered a grid traversal */
     uint64_t cells[RM_STAGE_SLOTS];
     uint64_t triangle_tests[RM_STAGE_SLOTS];
     uint64_t shaded_triangles[RM_STAGE_SLOTS];

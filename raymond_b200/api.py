@@ -100,12 +100,19 @@ class StatsC(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+KERNEL_KINDS = ("setup", "traverse", "shade", "accumulate")
+
+
 class StageStatsC(C.Structure):
-    _fields_ = [("ms", C.c_double * STAGE_SLOTS)] + [(n, C.c_uint64 * STAGE_SLOTS) for n in
-                                                      ("launches", "rays", "cells", "triangle_tests", "shaded_triangles")]
+    _fields_ = [("ms", (C.c_double * STAGE_SLOTS) * 4), ("launches", (C.c_uint64 * STAGE_SLOTS) * 4)] + \
+               [(n, C.c_uint64 * STAGE_SLOTS) for n in ("rays", "grid_rays", "cells", "triangle_tests", "shaded_triangles")]
 
     def as_dict(self) -> dict:
-        return {n: list(getattr(self, n)) for n, _ in self._fields_}
+        d = {"ms": {k: list(self.ms[i]) for i, k in enumerate(KERNEL_KINDS)},
+             "launches": {k: list(self.launches[i]) for i, k in enumerate(KERNEL_KINDS)}}
+        for n in ("rays", "grid_rays", "cells", "triangle_tests", "shaded_triangles"):
+            d[n] = list(getattr(self, n))
+        return d
 
 
 TILE_CALLBACK = C.CFUNCTYPE(None, C.POINTER(TileC), C.c_void_p)
@@ -624,7 +631,8 @@ class Renderer:
         return s.as_dict()
 
     def stage_stats(self) -> dict:
-        """Per wavefront stage: ms / launches (FLAG_STAGE_TIMING), rays, cells, triangle_tests, shaded_triangles (FLAG_COUNT_WORK)."""
+        """Per wavefront stage and kernel kind: ms / launches (FLAG_STAGE_TIMING); rays, grid_rays, shaded_triangles;
+        cells / triangle_tests (FLAG_COUNT_WORK)."""
         s = StageStatsC()
         _check(lib().rm_renderer_stage_stats(self._h, C.byref(s)))
         return s.as_dict()

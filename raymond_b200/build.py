@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libraymond_cuda.so")
 SOURCES = ["rm_host.cpp", "rm_task.cpp", "rm_device.cu"]
-HEADERS = ["rm_internal.hpp", os.path.join("..", "..", "include", "raymond.h")]
+HEADERS = ["rm_internal.hpp", "rm_kernels.cuh", os.path.join("..", "..", "include", "raymond.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -1,0 +1,751 @@
+// rm_kernels.cuh — device code of the hot path (sm_100a): data model, the bit-exact f64 intersection
+// routines, the counter-based RNG, camera, shading, and the wavefront kernels.
+//
+// One wavefront stage (= one recursion level of the reference's `trace`, src/trace.rs:232-320) is
+// three kernels, so that every warp does one kind of work:
+//   k_setup     one thread per ray: [camera ray generation |  queue read], the analytic objects
+//               (Sphere / Plane), AABB::intersects + DDA set-up of the grid; rays that enter a grid
+//               are appended (ballot/popc compaction) to a traversal queue of 128-byte records
+//   k_traverse  persistent warps over the traversal queue: AccGrid::intersects as a flattened state
+//               machine — each lane does ONE triangle test or ONE cell step per iteration and
+//               re-fills itself from the queue the moment its ray is finished
+//   k_shade     one thread per ray: surface normal, material, lobe choice, BRDF weight, next ray or
+//               delivered radiance; survivors are compacted into the next stage's ray queue
+// followed once per batch by k_accumulate (the tile accumulator).
+//
+// Build with -fmad=false: rustc never contracts a*b+c, and every f64 add/mul/div/sqrt below is one
+// IEEE operation in the reference's order.  Citations are relative to the reference checkout.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cfloat>
+
+#include "rm_internal.hpp"
+
+namespace rm {
+
+// ===================================================================== device data model
+
+constexpr int kMaxObjects = 64;   // objects carried in the kernel parameter block (constant bank)
+constexpr int kMaxGrids = 8;
+constexpr int kBlock = 256;
+
+// One AccGrid resident in HBM.
+//   cells : {first reference, count} per cell            (8 B, one 64-bit load per visited cell)
+//   refs  : triangle indices, ascending inside a cell     (4 B per reference)
+//   tri   : 96 B per triangle, 32 B aligned, 3 sectors: [v0.xyz v1.x][v1.yz v2.xy][v2.z 0 0 0]
+//   nrm   : 72 B per triangle (n0, n1, n2), read once per shaded hit
+struct DevGrid {
+    double bmin[3], bmax[3], cell[3];
+    int res[3];
+    int pad;
+    double diag2;             // squared diagonal of the bounding box (bounds the size of any triangle edge)
+    unsigned long long n_cells;
+    const uint2* cells;
+    const unsigned* refs;
+    const double* tri;
+    const double* nrm;
+};
+
+struct DevObject {
+    int geom;       // rm::GeometryKind
+    int mat;        // rm_material_kind
+    int grid;       // index into DevScene::grid
+    int pad;
+    double g[6];    // sphere: origin xyz, radius | plane: origin xyz, normal xyz
+    double color[3];// colour (Diffuse/Metal) or emitted radiance
+    double rough;
+};
+
+struct DevScene {
+    int n_objects;
+    int n_grids;
+    DevObject obj[kMaxObjects];
+    DevGrid grid[kMaxGrids];
+};
+
+struct DevCamera {
+    double pos[3];
+    double width, height, aspect, tan_half;   // tan(fov_vert / 2 * PI / 180), evaluated once on the host (glibc)
+    double focal_length, aperture_radius;
+    int W, H;
+    int use_dof;
+    int pad;
+};
+
+// Ray queue of one stage, SoA: ray (6), throughput (3), path slot.
+struct Queue {
+    double* f[9];
+    unsigned* id;
+};
+
+// Closest hit so far per ray of the current stage.
+struct HitArrays {
+    double* t;
+    int* obj;        // -1 = miss
+    unsigned* sub;
+};
+
+// Traversal queue: one 128-byte record per (ray, grid) pair that passed the AABB test:
+//   [o.xyz d.x] [d.yz tmax.xy] [tmax.z tdelta.xyz] [cell.x cell.y | cell.z stepbits | ray index, - | -]
+constexpr int kTravDoubles = 16;
+
+struct DevTotals {
+    unsigned long long samples, rays, nonfinite;
+    unsigned long long stage_rays[RM_STAGE_SLOTS], grid_rays[RM_STAGE_SLOTS], cells[RM_STAGE_SLOTS], tests[RM_STAGE_SLOTS], shaded[RM_STAGE_SLOTS];
+};
+
+// Per-batch device counters, all indexed by depth (zeroed once per batch).
+struct StageCounters {
+    unsigned* rays;       // rays[d]     = rays queued for depth d+1 (written by k_shade of depth d)
+    unsigned* trav;       // trav[d]     = traversal records of depth d
+    unsigned* cursor;     // cursor[d]   = fetch cursor of k_traverse at depth d
+};
+
+struct RenderParams {
+    DevCamera cam;
+    unsigned long long seed;
+    const unsigned* pixel_map;   // owned pixel q -> frame pixel index (y*W + x), warp = 8x4 block
+    unsigned n_pixels;           // owned pixels
+    unsigned first_sample, sample_stride;
+    unsigned bounce_limit;
+    unsigned cap;                // paths per batch (capacity of queues and of `contrib`)
+    double* contrib;             // 3 planes of `cap`: radiance each path delivered
+    StageCounters cnt;
+    DevTotals* totals;
+};
+
+__host__ __device__ inline unsigned stage_slot(unsigned depth) { return depth < RM_STAGE_SLOTS - 1 ? depth : RM_STAGE_SLOTS - 1; }
+
+// ===================================================================== device math (cgmath semantics)
+
+struct D3 { double x, y, z; };
+__device__ __forceinline__ D3 d3(double x, double y, double z) { D3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ D3 operator+(D3 a, D3 b) { return d3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ D3 operator-(D3 a, D3 b) { return d3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ D3 operator-(D3 a) { return d3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ D3 operator*(D3 a, double s) { return d3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ D3 operator*(double s, D3 a) { return d3(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ D3 operator/(D3 a, double s) { return d3(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ D3 mul(D3 a, D3 b) { return d3(a.x * b.x, a.y * b.y, a.z * b.z); }
+// Vector3::dot: products summed left to right
+__device__ __forceinline__ double dot(D3 a, D3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ D3 cross(D3 a, D3 b) { return d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+// InnerSpace::normalize: multiply by the reciprocal magnitude
+__device__ __forceinline__ D3 normalize(D3 a) { return a * (1.0 / sqrt(dot(a, a))); }
+__device__ __forceinline__ double dist(D3 a, D3 b) { D3 d = b - a; return sqrt(dot(d, d)); }
+// Matrix3::from_cols(c0, c1, c2) * v
+__device__ __forceinline__ D3 mat_mul(D3 c0, D3 c1, D3 c2, D3 v) { return (c0 * v.x + c1 * v.y) + c2 * v.z; }
+__device__ __forceinline__ D3 ld3(const double* p) { return d3(p[0], p[1], p[2]); }
+
+// 256-bit global accesses (LDG/STG.E.ENL2.256 on sm_100a)
+__device__ __forceinline__ void ld256_nc(const double* p, double& a, double& b, double& c, double& d) {
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ void ld256(const double* p, double& a, double& b, double& c, double& d) {
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st256(double* p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+// ===================================================================== intersection (bit-exact scope)
+
+// Sphere::intersects                                       primitives/sphere.rs:11-27
+__device__ __forceinline__ bool hit_sphere(const DevObject& s, D3 o, D3 d, double& t_out) {
+    D3 c = ld3(s.g) - o;
+    double t = dot(c, d);
+    D3 q = c - t * d;
+    double p = dot(q, q);
+    double r2 = s.g[3] * s.g[3];
+    if (p > r2) return false;
+    t -= sqrt(r2 - p);
+    if (t <= 0.0) return false;
+    t_out = t;
+    return true;
+}
+
+// Plane::intersects                                        primitives/plane.rs:11-24
+__device__ __forceinline__ bool hit_plane(D3 origin, D3 normal, D3 o, D3 d, double& t_out) {
+    double denom = dot(normal, -d);
+    if (denom > 1e-6) {
+        D3 p0l0 = origin - o;
+        double t = dot(p0l0, -normal) / denom;
+        if (t >= 0.0) { t_out = t; return true; }
+    }
+    return false;
+}
+
+// cgmath cast::<i32>(): Some(trunc) iff i32::MIN - 1 < v < i32::MAX + 1 (NaN fails)
+__device__ __forceinline__ bool cast_i32(double v, int& out) {
+    if (!(v > -2147483649.0 && v < 2147483648.0)) return false;
+    out = __double2int_rz(v);
+    return true;
+}
+
+// State of one ray inside AccGrid::intersects' loop (acc_grid.rs:127-184).
+struct Dda {
+    double tmx, tmy, tmz;   // t_max_{x,y,z}
+    double tdx, tdy, tdz;   // t_delta_{x,y,z}
+    int cx, cy, cz;         // current_cell
+    unsigned step;          // bit a set: step along axis a is -1 (else +1)
+};
+
+// AABB::intersects (aabb.rs:10-31) followed by the set-up half of AccGrid::intersects
+// (acc_grid.rs:90-125).  Returns false when the reference returns None before its loop (or would
+// panic on a failed cast).  `tmin_out` / `tmax_out` are the AABB entry (may be negative) and exit distances.
+// Quirks kept: only a NEGATIVE start cell is moved to the box entry point (A3); casts truncate
+// toward zero (A5); signum looks at the sign bit, so -0.0 steps backwards (A7).
+__device__ __forceinline__ bool grid_enter(const DevGrid& g, D3 o, D3 d, Dda& s, double& tmin_out, double& tmax_out) {
+    const double ix = 1.0 / d.x, iy = 1.0 / d.y, iz = 1.0 / d.z;
+    double t1 = (g.bmin[0] - o.x) * ix, t2 = (g.bmax[0] - o.x) * ix;
+    double tmin = fmin(t1, t2), tmax = fmax(t1, t2);
+    t1 = (g.bmin[1] - o.y) * iy; t2 = (g.bmax[1] - o.y) * iy;
+    tmin = fmax(tmin, fmin(t1, t2)); tmax = fmin(tmax, fmax(t1, t2));
+    t1 = (g.bmin[2] - o.z) * iz; t2 = (g.bmax[2] - o.z) * iz;
+    tmin = fmax(tmin, fmin(t1, t2)); tmax = fmin(tmax, fmax(t1, t2));
+    if (!(tmax > fmax(tmin, 0.0))) return false;
+    tmin_out = tmin;
+    tmax_out = tmax;
+
+    const double csx = g.cell[0], csy = g.cell[1], csz = g.cell[2];
+    double sx = o.x - g.bmin[0], sy = o.y - g.bmin[1], sz = o.z - g.bmin[2];
+    int cx, cy, cz;
+    if (!cast_i32(sx / csx, cx) || !cast_i32(sy / csy, cy) || !cast_i32(sz / csz, cz)) return false;
+    if (cx < 0 || cy < 0 || cz < 0) {
+        sx = (o.x + d.x * tmin) - g.bmin[0];   // outer_hit_position - bounding_box.min
+        sy = (o.y + d.y * tmin) - g.bmin[1];
+        sz = (o.z + d.z * tmin) - g.bmin[2];
+        if (!cast_i32(sx / csx, cx) || !cast_i32(sy / csy, cy) || !cast_i32(sz / csz, cz)) return false;
+    }
+    if (d.x != d.x || d.y != d.y || d.z != d.z) return false;   // signum(NaN).cast() fails
+    const bool nx = d.x < 0.0, ny = d.y < 0.0, nz = d.z < 0.0;
+    s.step = (__double2hiint(d.x) < 0 ? 1u : 0u) | (__double2hiint(d.y) < 0 ? 2u : 0u) | (__double2hiint(d.z) < 0 ? 4u : 0u);
+    s.tdx = (nx ? -csx : csx) / d.x;
+    s.tdy = (ny ? -csy : csy) / d.y;
+    s.tdz = (nz ? -csz : csz) / d.z;
+    s.tmx = (((double)(cx + (nx ? 0 : 1)) * csx) - sx) / d.x;
+    s.tmy = (((double)(cy + (ny ? 0 : 1)) * csy) - sy) / d.y;
+    s.tmz = (((double)(cz + (nz ? 0 : 1)) * csz) - sz) / d.z;
+    s.cx = cx; s.cy = cy; s.cz = cz;
+    return true;
+}
+
+// Cell index with the reference's z stride of res.z (A1); false when it is >= cells.len()
+// (acc_grid.rs:128-131: the traversal returns None).
+__device__ __forceinline__ bool grid_cell_index(const DevGrid& g, int cx, int cy, int cz, unsigned long long& idx) {
+    idx = (unsigned long long)(long long)cx +
+          (unsigned long long)g.res[0] * ((unsigned long long)(long long)cy + (unsigned long long)(long long)cz * (unsigned long long)g.res[2]);
+    return idx < g.n_cells;
+}
+
+// One step of the 3D-DDA (acc_grid.rs:155-183); ties go to the later axis (A4).  False = left the grid.
+__device__ __forceinline__ bool dda_step(const DevGrid& g, Dda& s) {
+    if (s.tmx < s.tmy) {
+        if (s.tmx < s.tmz) { s.cx += (s.step & 1u) ? -1 : 1; if (s.cx >= g.res[0] || s.cx < 0) return false; s.tmx += s.tdx; }
+        else               { s.cz += (s.step & 4u) ? -1 : 1; if (s.cz >= g.res[2] || s.cz < 0) return false; s.tmz += s.tdz; }
+    } else {
+        if (s.tmy < s.tmz) { s.cy += (s.step & 2u) ? -1 : 1; if (s.cy >= g.res[1] || s.cy < 0) return false; s.tmy += s.tdy; }
+        else               { s.cz += (s.step & 4u) ? -1 : 1; if (s.cz >= g.res[2] || s.cz < 0) return false; s.tmz += s.tdz; }
+    }
+    return true;
+}
+
+// Triangle::intersects (Moller-Trumbore, two-sided, eps 1e-8)     primitives/triangle.rs:11-44
+__device__ __forceinline__ bool hit_triangle(const double* __restrict__ tp, D3 o, D3 d, double& t_out) {
+    double v0x, v0y, v0z, v1x, v1y, v1z, v2x, v2y, v2z, p0, p1, p2;
+    ld256_nc(tp, v0x, v0y, v0z, v1x);
+    ld256_nc(tp + 4, v1y, v1z, v2x, v2y);
+    ld256_nc(tp + 8, v2z, p0, p1, p2);
+    const D3 e1 = d3(v1x - v0x, v1y - v0y, v1z - v0z);
+    const D3 e2 = d3(v2x - v0x, v2y - v0y, v2z - v0z);
+    const D3 h = cross(d, e2);
+    const double a = dot(e1, h);
+    if (a < 0.00000001 && a > -0.00000001) return false;
+    const double f = 1.0 / a;
+    const D3 s = d3(o.x - v0x, o.y - v0y, o.z - v0z);
+    const double u = f * dot(s, h);
+    if (u < 0.0 || u > 1.0) return false;
+    const D3 q = cross(s, e1);
+    const double v = f * dot(d, q);
+    if (v < 0.0 || u + v > 1.0) return false;
+    const double t = f * dot(e2, q);
+    if (!(t > 0.00000001)) return false;
+    t_out = t;
+    return true;
+}
+
+// Scene::intersect keeps the first object among equal distances (strict <, scene.rs:61).  Objects are
+// not visited in index order here (analytic ones first, grids after), so the same rule is applied in
+// its order-independent form: smaller distance wins, equal distances go to the lower object index.
+__device__ __forceinline__ bool closer(double t, int obj, double best_t, int best_obj) {
+    return best_obj < 0 || t < best_t || (t == best_t && obj < best_obj);
+}
+
+// ===================================================================== counter-based RNG
+// Philox4x32-10, key = seed, counter = (pixel, sample, depth, draw >> 1).  Draw `i` of
+// (pixel, sample, depth) stands in for the i-th rand::random::<f64>() the reference makes there.
+
+__device__ __forceinline__ void philox(unsigned long long seed, unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned w[4]) {
+    unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const unsigned h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const unsigned h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    w[0] = c0; w[1] = c1; w[2] = c2; w[3] = c3;
+}
+// 52 bits -> (k + 0.5) * 2^-52, strictly inside (0, 1)
+__device__ __forceinline__ double u52(unsigned hi, unsigned lo) {
+    const unsigned long long bits = ((unsigned long long)hi << 32) | lo;
+    return (__ull2double_rn(bits >> 12) + 0.5) * (1.0 / 4503599627370496.0);
+}
+
+// ===================================================================== camera
+
+// generate_primary_ray                                     src/trace.rs:322-333
+// jx, jy are the jitter terms (rand - 0.5).
+__device__ __forceinline__ D3 primary_direction(const DevCamera& c, unsigned xi, unsigned yi, double jx, double jy) {
+    const double x = (double)xi + jx;
+    const double y = (double)yi + jy;
+    const double px = (2.0 * ((x + 0.5) / c.width) - 1.0) * c.tan_half * c.aspect;
+    const double py = (1.0 - 2.0 * ((y + 0.5) / c.height)) * c.tan_half;
+    return normalize(d3(px, py, 1.0));
+}
+
+// generate_primary_ray / generate_primary_ray_with_dof     src/trace.rs:322-360
+__device__ __forceinline__ void camera_ray(const DevCamera& c, unsigned long long seed, unsigned pixel, unsigned sample, D3& o, D3& d) {
+    unsigned w[4];
+    philox(seed, pixel, sample, 0u, 0u, w);
+    const unsigned xi = pixel % (unsigned)c.W, yi = pixel / (unsigned)c.W;
+    const D3 cam = ld3(c.pos);
+    D3 dir = primary_direction(c, xi, yi, u52(w[0], w[1]) - 0.5, u52(w[2], w[3]) - 0.5);
+    if (!c.use_dof) { o = cam; d = dir; return; }
+    // rejection-sample the aperture disk (world XY at the camera's z)
+    D3 start;
+    for (unsigned j = 1;; j++) {
+        philox(seed, pixel, sample, 0u, j, w);
+        const double r1 = u52(w[0], w[1]) * 2.0 - 1.0;
+        const double r2 = u52(w[2], w[3]) * 2.0 - 1.0;
+        start = d3(cam.x + r1 * c.aperture_radius, cam.y + r2 * c.aperture_radius, cam.z);
+        if (dist(start, cam) < c.aperture_radius) break;
+    }
+    // focal plane: origin = cam + (0,0,1)*focal_length, normal (0,0,-1); Plane::intersects(primary).unwrap()
+    const D3 fo = cam + d3(0.0, 0.0, 1.0) * c.focal_length;
+    double t = 0.0;
+    hit_plane(fo, d3(0.0, 0.0, -1.0), cam, dir, t);
+    const D3 end = cam + t * dir;
+    o = start;
+    d = normalize(end - start);
+}
+
+// ===================================================================== shading (statistical scope)
+
+// create_coordinate_system_of_n                            src/trace.rs:408-416
+__device__ __forceinline__ void onb(D3 n, D3& t, D3& b) {
+    const double sign = n.z > 0.0 ? 1.0 : -1.0;
+    const double a = -1.0 / (sign + n.z);
+    const double bb = n.x * n.y * a;
+    t = d3(1.0 + sign * n.x * n.x * a, sign * bb, -sign * n.x);
+    b = d3(bb, sign + n.y * n.y * a, -n.y);
+}
+
+__device__ __forceinline__ double pow5(double x) { const double x2 = x * x; return x2 * x2 * x; }
+
+// Triangle::get_surface_properties (Heron-area barycentrics)    triangle.rs:47-68
+__device__ __forceinline__ double heron(D3 a, D3 b, D3 c) {
+    const double ab = dist(a, b), ac = dist(a, c), bc = dist(b, c);
+    const double s = (ab + ac + bc) / 2.0;
+    return sqrt(s * (s - ab) * (s - ac) * (s - bc));
+}
+__device__ __forceinline__ D3 triangle_normal(const DevGrid& g, unsigned ti, D3 p) {
+    const double* tp = g.tri + (size_t)ti * 12;
+    const D3 v0 = ld3(tp), v1 = ld3(tp + 3), v2 = ld3(tp + 6);
+    const double* np = g.nrm + (size_t)ti * 9;
+    const D3 n0 = ld3(np), n1 = ld3(np + 3), n2 = ld3(np + 6);
+    const double abc = heron(v0, v1, v2);
+    const double abp = heron(v0, v1, p);
+    const double bcp = heron(v0, v2, p);
+    const double ba = abp / abc, bb = bcp / abc;
+    const double bc = 1.0 - (ba + bb);
+    return normalize((n2 * ba) + (n1 * bb) + (n0 * bc));
+}
+
+// One bounce of `trace` (src/trace.rs:232-320) in throughput form: the recursion multiplies the
+// child radiance by a weight known before recursing, so a path's value is (prod of weights) (*)
+// emission.  Returns true when the path continues with (o, d, T) updated; otherwise `result` is
+// the radiance the path delivers.
+__device__ __forceinline__ bool shade(const DevScene& sc, const RenderParams& rp, double hit_t, int hit_obj, unsigned hit_sub, unsigned pixel,
+                                      unsigned sample, unsigned depth, D3& o, D3& d, D3& T, D3& result, unsigned& shaded_tri) {
+    result = d3(0.0, 0.0, 0.0);
+    if (hit_obj < 0) return false;                                          // :242
+    const DevObject& ob = sc.obj[hit_obj];
+    const D3 frag = o + d * hit_t;                                          // :246
+    if (ob.mat == RM_MATERIAL_EMISSION) { result = mul(T, ld3(ob.color)); return false; }   // :250
+    if (depth >= rp.bounce_limit) return false;                             // the child call returns 0 (:235-237)
+    D3 normal;                                                              // :244
+    if (ob.geom == GEOM_PLANE) normal = ld3(ob.g + 3);
+    else if (ob.geom == GEOM_SPHERE) normal = normalize(frag - ld3(ob.g));
+    else { normal = triangle_normal(sc.grid[ob.grid], hit_sub, frag); shaded_tri++; }
+
+    const D3 color = ld3(ob.color);
+    const double rough = ob.rough;
+    const double metal = ob.mat == RM_MATERIAL_METAL ? 1.0 : 0.0;
+    const D3 view = normalize(ld3(rp.cam.pos) - frag);                      // :256 (always the camera position)
+    const D3 f0 = d3(0.04 + metal * (color.x - 0.04), 0.04 + metal * (color.y - 0.04), 0.04 + metal * (color.z - 0.04));
+    unsigned w[4];
+    philox(rp.seed, pixel, sample, depth, 0u, w);
+    const double r = u52(w[0], w[1]);                                       // :260
+    const double ra = u52(w[2], w[3]);
+    philox(rp.seed, pixel, sample, depth, 1u, w);
+    const double rb = u52(w[0], w[1]);
+    const double prob_d = 0.5 + metal * (0.0 - 0.5);                        // :263
+    D3 wgt, dir;
+    double eps;
+    if (r < prob_d) {
+        // cosine-weighted hemisphere: theta = acos(sqrt(r1)), pdf = sqrt(r1)      :396-406
+        const double ct = sqrt(ra), st = sqrt(1.0 - ra);
+        double sp, cp;
+        sincos(2.0 * 3.14159265358979323846 * rb, &sp, &cp);
+        D3 tg, bt;
+        onb(normal, tg, bt);
+        dir = normalize(mat_mul(tg, normal, bt, d3(st * cp, ct, st * sp)));    // :266
+        const double cos_theta = fmax(dot(normal, dir), 0.0);                   // :275
+        const D3 half = normalize(dir + view);
+        const double fr = pow5(1.0 - fmax(dot(half, view), 0.0));               // :277
+        const D3 fres = f0 + (d3(1.0, 1.0, 1.0) - f0) * fr;
+        const D3 diff = (d3(1.0, 1.0, 1.0) - fres) * (1.0 - metal);
+        wgt = (mul(diff, color) * cos_theta) / (prob_d * ct);                   // :281-282
+        eps = 0.00001;                                                          // :269
+    } else {
+        const D3 refl = normalize(-view - 2.0 * (-dot(view, normal) * normal)); // :285
+        const double a = rough * rough;
+        const double phi = 2.0 * 3.14159265358979323846 * ra;
+        const double theta = a * sqrt(rb / (1.0 - rb));                         // :291 (used as an angle)
+        double sth, cth, sp, cp;
+        sincos(theta, &sth, &cth);
+        sincos(phi, &sp, &cp);
+        D3 tg, bt;
+        onb(refl, tg, bt);
+        dir = normalize(mat_mul(tg, refl, bt, d3(sth * cp, cth, sth * sp)));    // :295
+        const double cos_theta = dot(normal, dir);                              // :306
+        const D3 light = normalize(dir);
+        const D3 half = normalize(light + view);
+        const double hv = dot(half, view);
+        const D3 F = f0 + (d3(1.0, 1.0, 1.0) - f0) * pow5(1.0 - hv);            // :309
+        const double a2 = rough * rough;                                        // ggx_distribution :362-370
+        const double nh = dot(normal, half);
+        double den = (nh * nh) * (a2 - 1.0) + 1.0;
+        den = fmax(3.14159265358979323846 * den * den, 1e-7);
+        const double D = a2 / den;
+        const double k = (rough * rough) / 8.0;                                 // geometry_smith :372-382
+        const double nv = fmax(dot(normal, view), 0.0), nl = fmax(dot(normal, dir), 0.0);
+        const double G = (nv / (nv * (1.0 - k) + k)) * (nl / (nl * (1.0 - k) + k));
+        const D3 nom = (D * G) * F;
+        const double denom = 4.0 * dot(normal, view) * cos_theta + 0.001;       // :313
+        const double pdf = (D * nh) / (4.0 * hv) + 0.0001;                      // :317
+        wgt = (((nom / denom) * cos_theta) / (1.0 - prob_d)) / pdf;
+        eps = 0.0001;                                                           // :300
+    }
+    T = mul(T, wgt);
+    if (T.x == 0.0 && T.y == 0.0 && T.z == 0.0) return false;   // nothing downstream can change a zero path value
+    o = frag + normal * eps;
+    d = dir;
+    return true;
+}
+
+// ===================================================================== kernels
+
+enum RaySource : int { SRC_CAMERA = 0, SRC_QUEUE = 1, SRC_AOS = 2 };
+
+struct SetupArgs {
+    const double* q[6];        // SRC_QUEUE: ray SoA of this stage;  SRC_CAMERA: the same arrays, written here
+    const rm_ray* aos;         // SRC_AOS: caller's rays
+    const unsigned* n_ptr;     // number of rays (device) ...
+    unsigned n_direct;         // ... or, when n_ptr is null, this
+    HitArrays hit;
+    double* trav;              // traversal queue (kTravDoubles per record)
+    unsigned* trav_count;
+    int grid_object;           // object index of the grid this pass sets up, -1 = none
+    int analytic;              // 1: evaluate the Sphere/Plane objects and initialise the hit record
+};
+
+// Stage part 1.  See the header comment.
+template <int SRC>
+__global__ void __launch_bounds__(kBlock) k_setup(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
+                                                   const __grid_constant__ SetupArgs a) {
+    const unsigned n = a.n_ptr ? *a.n_ptr : a.n_direct;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned warps_total = (gridDim.x * blockDim.x) >> 5;
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (unsigned base = warp * 32u; base < n; base += warps_total * 32u) {
+        const unsigned i = base + lane;
+        bool push = false;
+        D3 o, d;
+        Dda s;
+        if (i < n) {
+            if (SRC == SRC_CAMERA) {
+                const unsigned q = i % rp.n_pixels, s_local = i / rp.n_pixels;
+                camera_ray(rp.cam, rp.seed, rp.pixel_map[q], rp.first_sample + s_local * rp.sample_stride, o, d);
+                double* const* w = const_cast<double* const*>(a.q);
+                w[0][i] = o.x; w[1][i] = o.y; w[2][i] = o.z; w[3][i] = d.x; w[4][i] = d.y; w[5][i] = d.z;
+            } else if (SRC == SRC_QUEUE) {
+                o = d3(a.q[0][i], a.q[1][i], a.q[2][i]);
+                d = d3(a.q[3][i], a.q[4][i], a.q[5][i]);
+            } else {
+                const double* r = reinterpret_cast<const double*>(a.aos + i);
+                o = d3(r[0], r[1], r[2]);
+                d = d3(r[3], r[4], r[5]);
+            }
+            double best_t = 0.0;
+            int best_obj = -1;
+            if (a.analytic) {
+                // Scene::intersect over the Sphere / Plane objects, in order, strict <   scene.rs:54-68
+                double closest = DBL_MAX;
+                for (int k = 0; k < sc.n_objects; k++) {
+                    const DevObject& ob = sc.obj[k];
+                    double t;
+                    bool got = false;
+                    if (ob.geom == GEOM_PLANE) got = hit_plane(ld3(ob.g), ld3(ob.g + 3), o, d, t);
+                    else if (ob.geom == GEOM_SPHERE) got = hit_sphere(ob, o, d, t);
+                    if (got && t < closest) { closest = t; best_t = t; best_obj = k; }
+                }
+                a.hit.t[i] = best_t;
+                a.hit.obj[i] = best_obj;
+                a.hit.sub[i] = 0u;
+            } else {
+                best_obj = a.hit.obj[i];
+                best_t = a.hit.t[i];
+            }
+            if (a.grid_object >= 0) {
+                const DevGrid& g = sc.grid[sc.obj[a.grid_object].grid];
+                double tmin, tmax;
+                push = grid_enter(g, o, d, s, tmin, tmax);
+                // Every triangle lies inside the box, so the true distance of any grid hit is >= the box
+                // entry distance.  If another object is already hit before the entry point by more than the
+                // worst-case error of a computed triangle distance, the grid cannot win the strict `<` of
+                // Scene::intersect and its traversal is skipped.  Error bound of Moller-Trumbore's t:
+                // eps * |o - v0| * |e|^2 / |a| with |a| >= 1e-8 (triangle.rs:21), |o - v0| <= tmax (|d| = 1),
+                // |e|^2 <= diag2  =>  <= 1.2e-8 * tmax * diag2; the margin below is 10x that plus 1e-6.
+                if (push && best_obj >= 0 && tmin > best_t + (1e-6 + 1e-7 * fabs(tmax) * g.diag2)) push = false;
+            }
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, push);
+        if (mask) {
+            unsigned pos = 0;
+            if (lane == 0) pos = atomicAdd(a.trav_count, (unsigned)__popc(mask));
+            pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(mask & ((1u << lane) - 1u));
+            if (push) {
+                double* rec = a.trav + (size_t)pos * kTravDoubles;
+                st256(rec, o.x, o.y, o.z, d.x);
+                st256(rec + 4, d.y, d.z, s.tmx, s.tmy);
+                st256(rec + 8, s.tmz, s.tdx, s.tdy, s.tdz);
+                st256(rec + 12, __hiloint2double(s.cy, s.cx), __hiloint2double((int)s.step, s.cz), __hiloint2double(0, (int)i), 0.0);
+            }
+        }
+    }
+}
+
+struct TraverseArgs {
+    const double* trav;
+    const unsigned* n_ptr;
+    unsigned* cursor;
+    HitArrays hit;
+    int grid_object;       // object index reported for hits
+    unsigned depth;        // for the work counters
+    DevTotals* totals;
+};
+
+// Stage part 2: AccGrid::intersects' loop (acc_grid.rs:127-184) for every queued ray.
+// Quirks kept: the first cell holding any hit returns its closest hit without an in-cell check (A2);
+// the per-cell closest starts at 5712515.0 (A6); leaving the grid or an out-of-range cell index is a miss.
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock, 2) k_traverse(const __grid_constant__ DevGrid g, const __grid_constant__ TraverseArgs a) {
+    const unsigned n = *a.n_ptr;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt = (1u << lane) - 1u;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.totals) atomicAdd(&a.totals->grid_rays[stage_slot(a.depth)], (unsigned long long)n);
+    bool active = false, done = false;
+    D3 o = d3(0, 0, 0), d = d3(0, 0, 0);
+    Dda s{};
+    unsigned ray = 0, k = 0, kend = 0, best = 0;
+    double closest = 5712515.0;
+    bool have = false;
+    unsigned n_cells = 0, n_tests = 0;
+    for (;;) {
+        // ---- refill: every idle lane takes the next record
+        const unsigned need = __ballot_sync(0xffffffffu, !active && !done);
+        if (need) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(a.cursor, (unsigned)__popc(need));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (!active && !done) {
+                const unsigned idx = base + __popc(need & lt);
+                if (idx >= n) {
+                    done = true;
+                } else {
+                    const double* rec = a.trav + (size_t)idx * kTravDoubles;
+                    double c0, c1, c2, c3;
+                    ld256(rec, o.x, o.y, o.z, d.x);
+                    ld256(rec + 4, d.y, d.z, s.tmx, s.tmy);
+                    ld256(rec + 8, s.tmz, s.tdx, s.tdy, s.tdz);
+                    ld256(rec + 12, c0, c1, c2, c3);
+                    s.cx = __double2loint(c0); s.cy = __double2hiint(c0);
+                    s.cz = __double2loint(c1); s.step = (unsigned)__double2hiint(c1);
+                    ray = (unsigned)__double2loint(c2);
+                    unsigned long long ci;
+                    if (grid_cell_index(g, s.cx, s.cy, s.cz, ci)) {
+                        const uint2 cell = __ldg(&g.cells[ci]);
+                        k = cell.x; kend = cell.x + cell.y;
+                        closest = 5712515.0; have = false;
+                        active = true;
+                        if (COUNT) { n_cells++; n_tests += cell.y; }
+                    }
+                    // else: the reference returns None at once; the lane stays idle and re-fills next round
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, !active)) {
+            if (__all_sync(0xffffffffu, done)) break;
+            continue;
+        }
+        // ---- one unit of work per lane
+        if (active) {
+            if (k < kend) {
+                const unsigned ti = __ldg(&g.refs[k]);
+                k++;
+                double t;
+                if (hit_triangle(g.tri + (size_t)ti * 12, o, d, t) && t < closest) { closest = t; best = ti; have = true; }
+            } else if (have) {
+                // the cell's closest hit is the grid's answer; merge with what the other objects found
+                if (closer(closest, a.grid_object, a.hit.t[ray], a.hit.obj[ray])) {
+                    a.hit.t[ray] = closest; a.hit.obj[ray] = a.grid_object; a.hit.sub[ray] = best;
+                }
+                active = false;
+            } else {
+                unsigned long long ci;
+                if (dda_step(g, s) && grid_cell_index(g, s.cx, s.cy, s.cz, ci)) {
+                    const uint2 cell = __ldg(&g.cells[ci]);
+                    k = cell.x; kend = cell.x + cell.y;
+                    closest = 5712515.0;
+                    if (COUNT) { n_cells++; n_tests += cell.y; }
+                } else {
+                    active = false;   // miss: the hit record keeps what the other objects found
+                }
+            }
+        }
+    }
+    if (COUNT) {
+        const unsigned c = __reduce_add_sync(0xffffffffu, n_cells), t = __reduce_add_sync(0xffffffffu, n_tests);
+        if (lane == 0) {
+            atomicAdd(&a.totals->cells[stage_slot(a.depth)], (unsigned long long)c);
+            atomicAdd(&a.totals->tests[stage_slot(a.depth)], (unsigned long long)t);
+        }
+    }
+}
+
+// Stage part 3: shade, then deliver radiance or append the next ray (warp-aggregated compaction).
+template <bool FIRST>
+__global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp, const Queue qin,
+                                                   const Queue qout, const HitArrays hit, const unsigned depth, const unsigned n_first) {
+    const unsigned n = FIRST ? n_first : rp.cnt.rays[depth - 1];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned warps_total = (gridDim.x * blockDim.x) >> 5;
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    unsigned shaded_tri = 0;
+    for (unsigned base = warp * 32u; base < n; base += warps_total * 32u) {
+        const unsigned i = base + lane;
+        bool cont = false;
+        D3 o, d, T;
+        unsigned slot = 0;
+        if (i < n) {
+            slot = FIRST ? i : qin.id[i];
+            o = d3(qin.f[0][i], qin.f[1][i], qin.f[2][i]);
+            d = d3(qin.f[3][i], qin.f[4][i], qin.f[5][i]);
+            T = FIRST ? d3(1.0, 1.0, 1.0) : d3(qin.f[6][i], qin.f[7][i], qin.f[8][i]);
+            const unsigned q = slot % rp.n_pixels, s_local = slot / rp.n_pixels;
+            const unsigned pixel = rp.pixel_map[q];
+            const unsigned sample = rp.first_sample + s_local * rp.sample_stride;
+            D3 result;
+            cont = shade(sc, rp, hit.t[i], hit.obj[i], hit.sub[i], pixel, sample, depth, o, d, T, result, shaded_tri);
+            if (!cont) {
+                rp.contrib[slot] = result.x;
+                rp.contrib[(size_t)rp.cap + slot] = result.y;
+                rp.contrib[2 * (size_t)rp.cap + slot] = result.z;
+            }
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, cont);
+        if (mask) {
+            unsigned pos = 0;
+            if (lane == 0) pos = atomicAdd(&rp.cnt.rays[depth], (unsigned)__popc(mask));
+            pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(mask & ((1u << lane) - 1u));
+            if (cont) {
+                qout.id[pos] = slot;
+                qout.f[0][pos] = o.x; qout.f[1][pos] = o.y; qout.f[2][pos] = o.z;
+                qout.f[3][pos] = d.x; qout.f[4][pos] = d.y; qout.f[5][pos] = d.z;
+                qout.f[6][pos] = T.x; qout.f[7][pos] = T.y; qout.f[8][pos] = T.z;
+            }
+        }
+    }
+    shaded_tri = __reduce_add_sync(0xffffffffu, shaded_tri);
+    if (lane == 0 && shaded_tri) atomicAdd(&rp.totals->shaded[stage_slot(depth)], (unsigned long long)shaded_tri);
+}
+
+// tile.data[..] += sample, one pass after the other          src/trace.rs:203
+// Adds the batch's per-path radiance to the running sums in global sample order, so the
+// association is the reference's ((0 + s0) + s1) + ...  Non-finite samples are dropped and counted
+// unless RM_FLAG_KEEP_NONFINITE.
+__global__ void __launch_bounds__(kBlock) k_accumulate(const __grid_constant__ RenderParams rp, double* __restrict__ accum,
+                                                        const unsigned n_batch_samples, const unsigned keep_nonfinite) {
+    DevTotals* totals = rp.totals;
+    const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned bad = 0;
+    if (q < rp.n_pixels) {
+        const size_t p = (size_t)rp.pixel_map[q] * 3;
+        double sx = accum[p], sy = accum[p + 1], sz = accum[p + 2];
+        for (unsigned s = 0; s < n_batch_samples; s++) {
+            const size_t k = (size_t)s * rp.n_pixels + q;
+            const double cx = rp.contrib[k], cy = rp.contrib[(size_t)rp.cap + k], cz = rp.contrib[2 * (size_t)rp.cap + k];
+            const bool finite = isfinite(cx) && isfinite(cy) && isfinite(cz);
+            if (!finite) bad++;
+            if (finite || keep_nonfinite) { sx += cx; sy += cy; sz += cz; }
+        }
+        accum[p] = sx; accum[p + 1] = sy; accum[p + 2] = sz;
+    }
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31u) == 0 && bad) atomicAdd(&totals->nonfinite, (unsigned long long)bad);
+    if (q == 0) {
+        unsigned long long rays = (unsigned long long)n_batch_samples * rp.n_pixels;
+        if (rp.bounce_limit) totals->stage_rays[1] += rays;
+        for (unsigned dpt = 1; dpt < rp.bounce_limit; dpt++) { rays += rp.cnt.rays[dpt]; totals->stage_rays[stage_slot(dpt + 1)] += rp.cnt.rays[dpt]; }
+        totals->rays += rp.bounce_limit ? rays : 0ull;
+        totals->samples += (unsigned long long)n_batch_samples * rp.n_pixels;
+    }
+}
+
+// Hit records -> the caller's Scene::intersect outputs (distance left untouched on a miss).
+__global__ void __launch_bounds__(kBlock) k_export_hits(const HitArrays hit, const size_t n, long long* __restrict__ obj,
+                                                         unsigned long long* __restrict__ sub, double* __restrict__ dist_out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int ob = hit.obj[i];
+        if (obj) obj[i] = ob;
+        if (sub) sub[i] = ob >= 0 ? hit.sub[i] : 0ull;
+        if (dist_out && ob >= 0) dist_out[i] = hit.t[i];
+    }
+}
+
+// generate_primary_ray with the jitter term forced to 0, whole frame, row-major.
+__global__ void __launch_bounds__(kBlock) k_primary_rays(const __grid_constant__ DevCamera cam, rm_ray* __restrict__ rays) {
+    const size_t n = (size_t)cam.W * cam.H;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const D3 d = primary_direction(cam, (unsigned)(i % cam.W), (unsigned)(i / cam.W), 0.0, 0.0);
+        double* r = reinterpret_cast<double*>(rays + i);
+        r[0] = cam.pos[0]; r[1] = cam.pos[1]; r[2] = cam.pos[2];
+        r[3] = d.x; r[4] = d.y; r[5] = d.z;
+    }
+}
+
+}  // namespace rm
