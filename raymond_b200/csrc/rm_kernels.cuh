@@ -562,84 +562,160 @@ struct TraverseArgs {
 // Stage part 2: AccGrid::intersects' loop (acc_grid.rs:127-184) for every queued ray.
 // Quirks kept: the first cell holding any hit returns its closest hit without an in-cell check (A2);
 // the per-cell closest starts at 5712515.0 (A6); leaving the grid or an out-of-range cell index is a miss.
+//
+// Persistent warps.  Every lane owns one ray's DDA state; the triangle tests are NOT tied to the lane
+// that owns the ray.  One loop iteration is three warp-uniform phases:
+//   A  lanes whose ray needs a cell walk the DDA (a bounded number of steps) to the next non-empty cell
+//   B  the triangle lists of all cells found are pooled: the warp's 32 lanes take (ray, reference) pairs
+//      from the pool round-robin, so every lane tests a triangle in every round, the reference and
+//      triangle fetches of a round are independent loads, and a ray's whole cell is tested in ~one L2
+//      round trip instead of one per triangle.  Per cell the winner is the smallest distance, ties to
+//      the earliest list position (the reference's strict `<` while walking the list in order)
+//   C  rays with a hit are finished (hit record merged), the others go back to A
+// Idle lanes re-fill from the traversal queue in groups.
+constexpr int kTravWarps = kBlock / 32;
+constexpr unsigned kTravMaxSteps = 6;     // DDA steps per phase A
+constexpr unsigned kRefillMin = 8;        // idle lanes that trigger a re-fill while others still have work
+
+struct TravWarpShared {
+    double ray[6][32];                 // o.xyz, d.xyz of the lane's ray
+    unsigned long long cand_t[32];     // this round's smallest distance bits per ray
+    unsigned cand_pos[32];             // ... and the earliest list position that has it
+    unsigned prefix[33];               // exclusive prefix of the pooled list lengths
+    unsigned kstart[32];               // first reference of the lane's cell
+};
+
+enum TravState : unsigned { TS_IDLE = 0, TS_LOOK = 1, TS_STEP = 2, TS_READY = 3 };
+
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlock, 2) k_traverse(const __grid_constant__ DevGrid g, const __grid_constant__ TraverseArgs a) {
+__global__ void __launch_bounds__(kBlock, 3) k_traverse(const __grid_constant__ DevGrid g, const __grid_constant__ TraverseArgs a) {
+    __shared__ TravWarpShared shared[kTravWarps];
+    TravWarpShared& sh = shared[threadIdx.x >> 5];
     const unsigned n = *a.n_ptr;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt = (1u << lane) - 1u;
+    const unsigned FULL = 0xffffffffu;
+    constexpr unsigned long long kClosest0 = 0x4155CAA0C0000000ull;   // bits of 5712515.0 (acc_grid.rs:135)
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.totals) atomicAdd(&a.totals->grid_rays[stage_slot(a.depth)], (unsigned long long)n);
-    bool active = false, done = false;
-    D3 o = d3(0, 0, 0), d = d3(0, 0, 0);
+
+    unsigned state = TS_IDLE;
+    bool exhausted = false;                 // the queue has no more records for this warp
     Dda s{};
-    unsigned ray = 0, k = 0, kend = 0, best = 0;
-    double closest = 5712515.0;
-    bool have = false;
+    unsigned ray = 0, k = 0, cnt = 0;
     unsigned n_cells = 0, n_tests = 0;
     for (;;) {
-        // ---- refill: every idle lane takes the next record
-        const unsigned need = __ballot_sync(0xffffffffu, !active && !done);
-        if (need) {
+        // ---- re-fill
+        const unsigned idle = __ballot_sync(FULL, state == TS_IDLE);
+        if (idle == FULL && exhausted) break;
+        if (!exhausted && (idle == FULL || __popc(idle) >= (int)kRefillMin)) {
             unsigned base = 0;
-            if (lane == 0) base = atomicAdd(a.cursor, (unsigned)__popc(need));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (!active && !done) {
-                const unsigned idx = base + __popc(need & lt);
-                if (idx >= n) {
-                    done = true;
-                } else {
+            if (lane == 0) base = atomicAdd(a.cursor, (unsigned)__popc(idle));
+            base = __shfl_sync(FULL, base, 0);
+            if (base + (unsigned)__popc(idle) >= n) exhausted = true;     // warp-uniform
+            if (state == TS_IDLE) {
+                const unsigned idx = base + __popc(idle & lt);
+                if (idx < n) {
                     const double* rec = a.trav + (size_t)idx * kTravDoubles;
-                    double c0, c1, c2, c3;
-                    ld256(rec, o.x, o.y, o.z, d.x);
-                    ld256(rec + 4, d.y, d.z, s.tmx, s.tmy);
+                    double ox, oy, oz, dx, dy, dz, c0, c1, c2, c3;
+                    ld256(rec, ox, oy, oz, dx);
+                    ld256(rec + 4, dy, dz, s.tmx, s.tmy);
                     ld256(rec + 8, s.tmz, s.tdx, s.tdy, s.tdz);
                     ld256(rec + 12, c0, c1, c2, c3);
                     s.cx = __double2loint(c0); s.cy = __double2hiint(c0);
                     s.cz = __double2loint(c1); s.step = (unsigned)__double2hiint(c1);
                     ray = (unsigned)__double2loint(c2);
-                    unsigned long long ci;
-                    if (grid_cell_index(g, s.cx, s.cy, s.cz, ci)) {
-                        const uint2 cell = __ldg(&g.cells[ci]);
-                        k = cell.x; kend = cell.x + cell.y;
-                        closest = 5712515.0; have = false;
-                        active = true;
-                        if (COUNT) { n_cells++; n_tests += cell.y; }
-                    }
-                    // else: the reference returns None at once; the lane stays idle and re-fills next round
+                    sh.ray[0][lane] = ox; sh.ray[1][lane] = oy; sh.ray[2][lane] = oz;
+                    sh.ray[3][lane] = dx; sh.ray[4][lane] = dy; sh.ray[5][lane] = dz;
+                    state = TS_LOOK;
                 }
             }
         }
-        if (__all_sync(0xffffffffu, !active)) {
-            if (__all_sync(0xffffffffu, done)) break;
-            continue;
+        // ---- A: walk to the next non-empty cell
+#pragma unroll 1
+        for (unsigned it = 0; it < kTravMaxSteps; it++) {
+            if (state == TS_LOOK || state == TS_STEP) {
+                unsigned long long ci;
+                if ((state == TS_LOOK || dda_step(g, s)) && grid_cell_index(g, s.cx, s.cy, s.cz, ci)) {
+                    const uint2 cell = __ldg(&g.cells[ci]);
+                    k = cell.x; cnt = cell.y;
+                    state = cnt ? TS_READY : TS_STEP;
+                    if (COUNT) { n_cells++; n_tests += cnt; }
+                } else {
+                    state = TS_IDLE;        // left the grid / index out of range: the reference returns None
+                }
+            }
+            if (!__any_sync(FULL, state == TS_LOOK || state == TS_STEP)) break;
         }
-        // ---- one unit of work per lane
-        if (active) {
-            if (k < kend) {
-                const unsigned ti = __ldg(&g.refs[k]);
-                k++;
+        // ---- B: pooled triangle tests of every ready cell
+        const unsigned mine = state == TS_READY ? cnt : 0u;
+        unsigned incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(FULL, incl, o);
+            if ((int)lane >= o) incl += v;
+        }
+        const unsigned total = __shfl_sync(FULL, incl, 31);
+        if (total == 0) continue;
+        if (lane == 0) sh.prefix[0] = 0u;
+        sh.prefix[lane + 1] = incl;
+        sh.kstart[lane] = k;
+        sh.cand_t[lane] = ~0ull;
+        sh.cand_pos[lane] = ~0u;
+        unsigned long long best_t = kClosest0;       // per-cell closest of MY ray
+        unsigned best_pos = ~0u;
+        __syncwarp();
+        for (unsigned base = 0; base < total; base += 32u) {
+            const unsigned item = base + lane;
+            bool got = false;
+            unsigned owner = 0, pos = 0;
+            unsigned long long tb = 0;
+            if (item < total) {
+                // owner = last lane whose exclusive prefix is <= item
+                unsigned lo = 0;
+#pragma unroll
+                for (unsigned w = 16; w; w >>= 1)
+                    if (sh.prefix[lo + w] <= item) lo += w;
+                owner = lo;
+                pos = sh.kstart[owner] + (item - sh.prefix[owner]);
+                const unsigned ti = __ldg(&g.refs[pos]);
+                const D3 o = d3(sh.ray[0][owner], sh.ray[1][owner], sh.ray[2][owner]);
+                const D3 d = d3(sh.ray[3][owner], sh.ray[4][owner], sh.ray[5][owner]);
                 double t;
-                if (hit_triangle(g.tri + (size_t)ti * 12, o, d, t) && t < closest) { closest = t; best = ti; have = true; }
-            } else if (have) {
+                if (hit_triangle(g.tri + (size_t)ti * 12, o, d, t)) {
+                    tb = (unsigned long long)__double_as_longlong(t);      // t > 1e-8: bit order = numeric order
+                    got = true;
+                    atomicMin(&sh.cand_t[owner], tb);
+                }
+            }
+            if (__any_sync(FULL, got)) {
+                __syncwarp();
+                if (got && sh.cand_t[owner] == tb) atomicMin(&sh.cand_pos[owner], pos);
+                __syncwarp();
+                // strict < against the earlier rounds (they hold earlier list positions) and against 5712515.0
+                const unsigned long long ct = sh.cand_t[lane];
+                if (ct < best_t) { best_t = ct; best_pos = sh.cand_pos[lane]; }
+                sh.cand_t[lane] = ~0ull;
+                sh.cand_pos[lane] = ~0u;
+                __syncwarp();
+            }
+        }
+        // ---- C
+        if (state == TS_READY) {
+            if (best_pos != ~0u) {
+                const double closest = __longlong_as_double((long long)best_t);
                 // the cell's closest hit is the grid's answer; merge with what the other objects found
                 if (closer(closest, a.grid_object, a.hit.t[ray], a.hit.obj[ray])) {
-                    a.hit.t[ray] = closest; a.hit.obj[ray] = a.grid_object; a.hit.sub[ray] = best;
+                    a.hit.t[ray] = closest; a.hit.obj[ray] = a.grid_object; a.hit.sub[ray] = __ldg(&g.refs[best_pos]);
                 }
-                active = false;
+                state = TS_IDLE;
             } else {
-                unsigned long long ci;
-                if (dda_step(g, s) && grid_cell_index(g, s.cx, s.cy, s.cz, ci)) {
-                    const uint2 cell = __ldg(&g.cells[ci]);
-                    k = cell.x; kend = cell.x + cell.y;
-                    closest = 5712515.0;
-                    if (COUNT) { n_cells++; n_tests += cell.y; }
-                } else {
-                    active = false;   // miss: the hit record keeps what the other objects found
-                }
+                state = TS_STEP;
             }
         }
+        __syncwarp();       // shared rays / prefix are rewritten by the next iteration
     }
     if (COUNT) {
-        const unsigned c = __reduce_add_sync(0xffffffffu, n_cells), t = __reduce_add_sync(0xffffffffu, n_tests);
+        const unsigned c = __reduce_add_sync(FULL, n_cells), t = __reduce_add_sync(FULL, n_tests);
         if (lane == 0) {
             atomicAdd(&a.totals->cells[stage_slot(a.depth)], (unsigned long long)c);
             atomicAdd(&a.totals->tests[stage_slot(a.depth)], (unsigned long long)t);
