@@ -39,16 +39,18 @@ def needs_build() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB) -> str:
+    """`defines` / `out` build a tuning variant (e.g. defines=["RM_TRAV_MAX_STEPS=12"], out=".../variant.so")."""
+    if not force and out == LIB and not needs_build():
         return LIB
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, f) for f in SOURCES] + ["-o", LIB]
+    cmd = [nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + \
+          [os.path.join(CSRC, f) for f in SOURCES] + ["-o", out]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libraymond_cuda.so")
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -128,13 +128,20 @@ static int upload_grid(rm_device_scene* ds, const Grid& g, DevGrid* out) {
     d.n_cells = g.n_cells();
     const size_t nc = (size_t)d.n_cells, nt = g.triangles.size();
     Pinned<uint2> cells;
-    Pinned<unsigned> refs;
+    Pinned<unsigned> refs, occ;
     Pinned<double> tri, nrm;
+    const size_t n_occ = (nc + 31) / 32;
     if (int st = cells.alloc(nc)) return st;
+    if (int st = occ.alloc(n_occ)) return st;
     if (int st = refs.alloc(g.references.size())) return st;
     if (int st = tri.alloc(nt * 12)) return st;
     if (int st = nrm.alloc(nt * 9)) return st;
-    for (size_t c = 0; c < nc; c++) cells.p[c] = make_uint2(g.cell_start[c], g.cell_start[c + 1] - g.cell_start[c]);
+    memset(occ.p, 0, n_occ * sizeof(unsigned));
+    for (size_t c = 0; c < nc; c++) {
+        const unsigned count = g.cell_start[c + 1] - g.cell_start[c];
+        cells.p[c] = make_uint2(g.cell_start[c], count);
+        if (count) occ.p[c >> 5] |= 1u << (c & 31);
+    }
     if (!g.references.empty()) memcpy(refs.p, g.references.data(), g.references.size() * sizeof(unsigned));
     for (size_t i = 0; i < nt; i++) {
         const rm_triangle& t = g.triangles[i];
@@ -146,6 +153,7 @@ static int upload_grid(rm_device_scene* ds, const Grid& g, DevGrid* out) {
         tri.p[i * 12 + 9] = tri.p[i * 12 + 10] = tri.p[i * 12 + 11] = 0.0;
     }
     if (int st = upload(ds, cells, &d.cells)) return st;
+    if (int st = upload(ds, occ, &d.occ)) return st;
     if (int st = upload(ds, refs, &d.refs)) return st;
     if (int st = upload(ds, tri, &d.tri)) return st;
     if (int st = upload(ds, nrm, &d.nrm)) return st;

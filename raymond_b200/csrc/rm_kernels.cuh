@@ -36,6 +36,8 @@ constexpr int kBlock = 256;
 //   refs  : triangle indices, ascending inside a cell     (4 B per reference)
 //   tri   : 96 B per triangle, 32 B aligned, 3 sectors: [v0.xyz v1.x][v1.yz v2.xy][v2.z 0 0 0]
 //   nrm   : 72 B per triangle (n0, n1, n2), read once per shaded hit
+//   occ   : 1 bit per cell, set when the cell holds any reference — 64x smaller than `cells`, so the walk
+//           through empty cells (most of a ray's cells) is served from L1 instead of one L2 trip per cell
 struct DevGrid {
     double bmin[3], bmax[3], cell[3];
     int res[3];
@@ -43,6 +45,7 @@ struct DevGrid {
     double diag2;             // squared diagonal of the bounding box (bounds the size of any triangle edge)
     unsigned long long n_cells;
     const uint2* cells;
+    const unsigned* occ;
     const unsigned* refs;
     const double* tri;
     const double* nrm;
@@ -241,30 +244,40 @@ __device__ __forceinline__ bool grid_cell_index(const DevGrid& g, int cx, int cy
 }
 
 // One step of the 3D-DDA (acc_grid.rs:155-183); ties go to the later axis (A4).  False = left the grid.
+// Written with selects instead of the reference's four branches: the lanes of a warp step along different
+// axes, and the arithmetic of the chosen axis (one compare pair, one integer add, one f64 add) is the same.
 __device__ __forceinline__ bool dda_step(const DevGrid& g, Dda& s) {
-    if (s.tmx < s.tmy) {
-        if (s.tmx < s.tmz) { s.cx += (s.step & 1u) ? -1 : 1; if (s.cx >= g.res[0] || s.cx < 0) return false; s.tmx += s.tdx; }
-        else               { s.cz += (s.step & 4u) ? -1 : 1; if (s.cz >= g.res[2] || s.cz < 0) return false; s.tmz += s.tdz; }
-    } else {
-        if (s.tmy < s.tmz) { s.cy += (s.step & 2u) ? -1 : 1; if (s.cy >= g.res[1] || s.cy < 0) return false; s.tmy += s.tdy; }
-        else               { s.cz += (s.step & 4u) ? -1 : 1; if (s.cz >= g.res[2] || s.cz < 0) return false; s.tmz += s.tdz; }
-    }
+    const bool xy = s.tmx < s.tmy, xz = s.tmx < s.tmz, yz = s.tmy < s.tmz;
+    const bool ax = xy && xz;              // x
+    const bool ay = !xy && yz;             // y; otherwise z
+    const unsigned bit = ax ? 1u : (ay ? 2u : 4u);
+    const int dir = (s.step & bit) ? -1 : 1;
+    const int c = (ax ? s.cx : (ay ? s.cy : s.cz)) + dir;
+    const int r = ax ? g.res[0] : (ay ? g.res[1] : g.res[2]);
+    if (c >= r || c < 0) return false;
+    const double tm = (ax ? s.tmx : (ay ? s.tmy : s.tmz)) + (ax ? s.tdx : (ay ? s.tdy : s.tdz));
+    if (ax) { s.cx = c; s.tmx = tm; } else if (ay) { s.cy = c; s.tmy = tm; } else { s.cz = c; s.tmz = tm; }
     return true;
 }
 
 // Triangle::intersects (Moller-Trumbore, two-sided, eps 1e-8)     primitives/triangle.rs:11-44
-__device__ __forceinline__ bool hit_triangle(const double* __restrict__ tp, D3 o, D3 d, double& t_out) {
-    double v0x, v0y, v0z, v1x, v1y, v1z, v2x, v2y, v2z, p0, p1, p2;
-    ld256_nc(tp, v0x, v0y, v0z, v1x);
-    ld256_nc(tp + 4, v1y, v1z, v2x, v2y);
-    ld256_nc(tp + 8, v2z, p0, p1, p2);
-    const D3 e1 = d3(v1x - v0x, v1y - v0y, v1z - v0z);
-    const D3 e2 = d3(v2x - v0x, v2y - v0y, v2z - v0z);
+struct TriPos { double v0x, v0y, v0z, v1x, v1y, v1z, v2x, v2y, v2z; };
+__device__ __forceinline__ TriPos load_triangle(const double* __restrict__ tp) {
+    TriPos p;
+    double p0, p1, p2;
+    ld256_nc(tp, p.v0x, p.v0y, p.v0z, p.v1x);
+    ld256_nc(tp + 4, p.v1y, p.v1z, p.v2x, p.v2y);
+    ld256_nc(tp + 8, p.v2z, p0, p1, p2);
+    return p;
+}
+__device__ __forceinline__ bool hit_triangle(const TriPos& p, D3 o, D3 d, double& t_out) {
+    const D3 e1 = d3(p.v1x - p.v0x, p.v1y - p.v0y, p.v1z - p.v0z);
+    const D3 e2 = d3(p.v2x - p.v0x, p.v2y - p.v0y, p.v2z - p.v0z);
     const D3 h = cross(d, e2);
     const double a = dot(e1, h);
     if (a < 0.00000001 && a > -0.00000001) return false;
     const double f = 1.0 / a;
-    const D3 s = d3(o.x - v0x, o.y - v0y, o.z - v0z);
+    const D3 s = d3(o.x - p.v0x, o.y - p.v0y, o.z - p.v0z);
     const double u = f * dot(s, h);
     if (u < 0.0 || u > 1.0) return false;
     const D3 q = cross(s, e1);
@@ -574,11 +587,20 @@ struct TraverseArgs {
 //   C  rays with a hit are finished (hit record merged), the others go back to A
 // Idle lanes re-fill from the traversal queue in groups.
 constexpr int kTravWarps = kBlock / 32;
-constexpr unsigned kTravMaxSteps = 6;     // DDA steps per phase A
-constexpr unsigned kRefillMin = 8;        // idle lanes that trigger a re-fill while others still have work
+#ifndef RM_TRAV_MAX_STEPS
+#define RM_TRAV_MAX_STEPS 6
+#endif
+#ifndef RM_TRAV_REFILL_MIN
+#define RM_TRAV_REFILL_MIN 8
+#endif
+#ifndef RM_TRAV_BLOCKS_PER_SM
+#define RM_TRAV_BLOCKS_PER_SM 3
+#endif
+constexpr unsigned kTravMaxSteps = RM_TRAV_MAX_STEPS;     // DDA steps per phase A
+constexpr unsigned kRefillMin = RM_TRAV_REFILL_MIN;       // idle lanes that trigger a re-fill while others still have work
 
 struct TravWarpShared {
-    double ray[6][32];                 // o.xyz, d.xyz of the lane's ray
+    double2 ray[32][3];                // {o.x o.y} {o.z d.x} {d.y d.z} of the lane's ray (three 128-bit accesses)
     unsigned long long cand_t[32];     // this round's smallest distance bits per ray
     unsigned cand_pos[32];             // ... and the earliest list position that has it
     unsigned prefix[33];               // exclusive prefix of the pooled list lengths
@@ -588,7 +610,7 @@ struct TravWarpShared {
 enum TravState : unsigned { TS_IDLE = 0, TS_LOOK = 1, TS_STEP = 2, TS_READY = 3 };
 
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlock, 3) k_traverse(const __grid_constant__ DevGrid g, const __grid_constant__ TraverseArgs a) {
+__global__ void __launch_bounds__(kBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(const __grid_constant__ DevGrid g, const __grid_constant__ TraverseArgs a) {
     __shared__ TravWarpShared shared[kTravWarps];
     TravWarpShared& sh = shared[threadIdx.x >> 5];
     const unsigned n = *a.n_ptr;
@@ -624,8 +646,9 @@ __global__ void __launch_bounds__(kBlock, 3) k_traverse(const __grid_constant__ 
                     s.cx = __double2loint(c0); s.cy = __double2hiint(c0);
                     s.cz = __double2loint(c1); s.step = (unsigned)__double2hiint(c1);
                     ray = (unsigned)__double2loint(c2);
-                    sh.ray[0][lane] = ox; sh.ray[1][lane] = oy; sh.ray[2][lane] = oz;
-                    sh.ray[3][lane] = dx; sh.ray[4][lane] = dy; sh.ray[5][lane] = dz;
+                    sh.ray[lane][0] = make_double2(ox, oy);
+                    sh.ray[lane][1] = make_double2(oz, dx);
+                    sh.ray[lane][2] = make_double2(dy, dz);
                     state = TS_LOOK;
                 }
             }
@@ -636,10 +659,14 @@ __global__ void __launch_bounds__(kBlock, 3) k_traverse(const __grid_constant__ 
             if (state == TS_LOOK || state == TS_STEP) {
                 unsigned long long ci;
                 if ((state == TS_LOOK || dda_step(g, s)) && grid_cell_index(g, s.cx, s.cy, s.cz, ci)) {
-                    const uint2 cell = __ldg(&g.cells[ci]);
-                    k = cell.x; cnt = cell.y;
-                    state = cnt ? TS_READY : TS_STEP;
-                    if (COUNT) { n_cells++; n_tests += cnt; }
+                    state = TS_STEP;
+                    if (COUNT) n_cells++;
+                    if ((__ldg(&g.occ[ci >> 5]) >> (ci & 31u)) & 1u) {
+                        const uint2 cell = __ldg(&g.cells[ci]);
+                        k = cell.x; cnt = cell.y;
+                        state = TS_READY;
+                        if (COUNT) n_tests += cnt;
+                    }
                 } else {
                     state = TS_IDLE;        // left the grid / index out of range: the reference returns None
                 }
@@ -664,32 +691,39 @@ __global__ void __launch_bounds__(kBlock, 3) k_traverse(const __grid_constant__ 
         unsigned long long best_t = kClosest0;       // per-cell closest of MY ray
         unsigned best_pos = ~0u;
         __syncwarp();
-        for (unsigned base = 0; base < total; base += 32u) {
-            const unsigned item = base + lane;
-            bool got = false;
-            unsigned owner = 0, pos = 0;
-            unsigned long long tb = 0;
-            if (item < total) {
-                // owner = last lane whose exclusive prefix is <= item
-                unsigned lo = 0;
+        // item -> (owner lane, list position, triangle): owner = last lane whose exclusive prefix is <= item
+        auto locate = [&](unsigned item, unsigned& owner, unsigned& pos, unsigned& ti) {
+            unsigned lo = 0;
 #pragma unroll
-                for (unsigned w = 16; w; w >>= 1)
-                    if (sh.prefix[lo + w] <= item) lo += w;
-                owner = lo;
-                pos = sh.kstart[owner] + (item - sh.prefix[owner]);
-                const unsigned ti = __ldg(&g.refs[pos]);
-                const D3 o = d3(sh.ray[0][owner], sh.ray[1][owner], sh.ray[2][owner]);
-                const D3 d = d3(sh.ray[3][owner], sh.ray[4][owner], sh.ray[5][owner]);
+            for (unsigned w = 16; w; w >>= 1)
+                if (sh.prefix[lo + w] <= item) lo += w;
+            owner = lo;
+            pos = sh.kstart[lo] + (item - sh.prefix[lo]);
+            ti = __ldg(&g.refs[pos]);
+        };
+        unsigned owner = 0, pos = 0, ti = 0;
+        if (lane < total) locate(lane, owner, pos, ti);
+        for (unsigned base = 0; base < total; base += 32u) {
+            const bool valid = base + lane < total;
+            bool got = false;
+            unsigned long long tb = 0;
+            const unsigned c_owner = owner, c_pos = pos;
+            TriPos tp;
+            if (valid) tp = load_triangle(g.tri + (size_t)ti * 12);
+            // the next round's reference is fetched while this round's triangle is in flight
+            if (base + 32u + lane < total) locate(base + 32u + lane, owner, pos, ti);
+            if (valid) {
+                const double2 r0 = sh.ray[c_owner][0], r1 = sh.ray[c_owner][1], r2 = sh.ray[c_owner][2];
                 double t;
-                if (hit_triangle(g.tri + (size_t)ti * 12, o, d, t)) {
+                if (hit_triangle(tp, d3(r0.x, r0.y, r1.x), d3(r1.y, r2.x, r2.y), t)) {
                     tb = (unsigned long long)__double_as_longlong(t);      // t > 1e-8: bit order = numeric order
                     got = true;
-                    atomicMin(&sh.cand_t[owner], tb);
+                    atomicMin(&sh.cand_t[c_owner], tb);
                 }
             }
             if (__any_sync(FULL, got)) {
                 __syncwarp();
-                if (got && sh.cand_t[owner] == tb) atomicMin(&sh.cand_pos[owner], pos);
+                if (got && sh.cand_t[c_owner] == tb) atomicMin(&sh.cand_pos[c_owner], c_pos);
                 __syncwarp();
                 // strict < against the earlier rounds (they hold earlier list positions) and against 5712515.0
                 const unsigned long long ct = sh.cand_t[lane];
