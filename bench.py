@@ -32,7 +32,10 @@ import numpy as np
 METRIC = "Msamples/sec (paths x 5 bounces), GoldDragon 1920x1080 500 spp"
 UNIT = "Msamples/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, from the ncu --set full capture in profiles/ (None = not captured)
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {
+    # profiles/r1_v4_traverse_ncu_summary.md: k_traverse launches of depth 1, 2, 3 of one 4-spp batch read+wrote 0.498 / 1.080 / 0.657 GB
+    "k_traverse": 0.745e9,
+}
 
 
 def log(*a):
@@ -215,6 +218,8 @@ def bench_ours(args):
         raise SystemExit("bench.py: no CUDA device — this implementation has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL would print its banner on stdout, next to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     B.build()
 
@@ -328,8 +333,10 @@ def bench_ours(args):
                     "unit_name": "grid ray" if top == "traverse" else ("path" if top == "accumulate" else "ray"),
                     "launch_ms_avg": pk["ms"] / max(pk["launches"], 1), "launches": pk["launches"], "share_of_step": pk["ms"] / max(total_ms, 1e-9),
                     "per_kernel_share": {"k_" + k: v["ms"] / max(total_ms, 1e-9) for k, v in per_kernel.items()},
-                    "note": "f64 no-FMA traversal of an L2-resident grid: bound by FP64 issue + L2 latency, not by HBM; "
-                            "see DESIGN.md and profiles/ for the ncu counters"}
+                    "traffic_note": "ncu dram bytes per launch (depths 1-3 of a 4-spp batch); far BELOW the algorithmic bytes because the "
+                                    "150 MB traversal set is L2-resident and every triangle is fetched by many rays (L2 hit 85-89 %)",
+                    "note": "f64 no-FMA traversal of an L2-resident grid: the binding limits are instruction issue (ncu: 50-55 % issue-active, "
+                            "FP64 pipe 19-21 %, LSU data pipe 59 %) and L2 latency, not HBM (3-7 % of peak); see DESIGN.md section 6 and profiles/"}
     dr.close()
     del dr
 

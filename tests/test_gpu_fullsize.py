@@ -1,0 +1,83 @@
+"""GPU parity at BASELINE.json's full sizes.
+
+configs[1] (GoldDragon 1920x1080, the 871 200-triangle stand-in) and configs[3] (1 M-triangle soup, 1920x1080
+primaries + 2^21 random rays).  The bit-exact scope is still compared ray for ray against the oracle (it finishes
+in seconds with all host threads); the render is checked through size-independent properties — batching
+invariance, additivity of the sample partition — and a same-stream oracle render at low spp."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from raymond_b200 import api as A
+from raymond_b200 import fixtures as F
+
+from util import assert_hits_equal, oracle_scene, product_scene, settings
+
+pytestmark = pytest.mark.gpu
+
+THREADS = os.cpu_count() or 8
+
+
+@pytest.fixture(scope="module")
+def dragon():
+    objs = F.gold_dragon(F.dragon_standin())
+    return objs, product_scene(objs), oracle_scene(objs)
+
+
+def test_gold_dragon_full_frame_primary_hits(dragon):
+    """north_star (a): every primary ray of the 1920x1080 frame reports the oracle's object, triangle and distance bits."""
+    objs, ps, os_ = dragon
+    cam = F.camera(1920, 1080)
+    rays = O.primary_rays(cam)
+    want = os_.intersect(rays, threads=THREADS)
+    got = ps.intersect(rays)
+    assert_hits_equal(got, want, "GoldDragon 1920x1080 primaries")
+    assert (want[0] == 1).sum() > 200_000                      # the mesh covers a good part of the frame
+    # jittered camera rays of sample 0 (what the renderer traces) as well
+    jr = O.camera_rays(cam, 2026, 0)
+    assert_hits_equal(ps.intersect(jr), os_.intersect(jr, threads=THREADS), "GoldDragon 1920x1080 jittered primaries")
+
+
+def test_gold_dragon_full_frame_render_properties(dragon):
+    objs, ps, os_ = dragon
+    cam, spp, seed = F.camera(1920, 1080), 4, 2026
+    st = settings(cam, spp)
+
+    def render(**kw):
+        r = A.Renderer(ps, st, A.GpuOptions(seed=seed, batch_spp=kw.get("batch_spp", 0)))
+        r.render(kw.get("first", 0), kw.get("count", spp), kw.get("stride", 1))
+        sums, stats = r.read_sums(), r.stats()
+        r.close()
+        return sums, stats
+
+    full, stats = render()
+    assert stats["samples"] == 1920 * 1080 * spp and stats["nonfinite_samples"] == 0
+    assert np.isfinite(full).all()
+    # batching is invisible (fixed summation order)
+    assert np.array_equal(render(batch_spp=1)[0], full)
+    # sample partition: rank 0 + rank 1 of 2 add up to the full frame
+    a, _ = render(first=0, count=2, stride=2)
+    b, _ = render(first=1, count=2, stride=2)
+    assert np.allclose(a + b, full, rtol=1e-12, atol=1e-12)
+    # same-stream oracle render: pixel sums agree to 1e-9 relative on all but a sliver of the frame
+    want, cnt = O.render(os_, cam, spp, seed=seed, worker_count=THREADS)
+    rel = np.abs(full - want).max(axis=-1) / np.maximum(np.abs(want).max(axis=-1), 1e-3 * spp)
+    assert (rel > 1e-9).mean() < 0.01, f"{(rel > 1e-9).mean():.3%} of the pixels differ"
+    lum = np.array([0.2126, 0.7152, 0.0722])
+    gl, ol = (np.clip(full / spp, 0, 10) @ lum).mean(), (np.clip(want / spp, 0, 10) @ lum).mean()
+    assert abs(gl - ol) <= 0.002 * ol
+
+
+@pytest.mark.parametrize("box", ["cubic", "flat"])
+def test_soup_1m_hit_indices(box):
+    """configs[3] at 1 M triangles: 1920x1080 pixel-centre primaries + 2^21 random rays, indices and distance bits."""
+    tris = F.triangle_soup(1_000_000, F.SOUP_BOX_CUBIC if box == "cubic" else F.SOUP_BOX_FLAT)
+    objs = F.soup_scene(tris)
+    del tris
+    rays = np.concatenate([O.primary_rays(F.camera(1920, 1080)), F.random_rays(1 << 21)])
+    want = oracle_scene(objs).intersect(rays, threads=THREADS)
+    got = product_scene(objs).intersect(rays)
+    assert_hits_equal(got, want, f"1M soup {box}")
+    assert (want[0] >= 0).mean() > 0.1
