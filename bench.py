@@ -392,7 +392,7 @@ def bench_ours(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{label} {W}x{H}, {spp} spp per GPU ({total_spp} total), {args.bounces} bounces", "scene": args.scene,
                        "spp_per_gpu": spp, "bounces": args.bounces, "tile": [32, 32], "parallelism": f"sample-split x{world} + ncclReduce(sum)",
-                       "l2": "inputs exceed L2 (scene ~180 MB + 1.4 GB of wavefront queues per batch); no explicit flush",
+                       "l2": "inputs exceed L2 (scene ~250 MB + ~10 GB of wavefront queues per 16-spp batch); no explicit flush",
                        "mesh": "stand-in" if args.scene == "gold_dragon" else "analytic"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "mrays_per_s": rays * world / ms_total / 1e3 if world == 1 else None, "rays_per_path": rays / max(samples_total / world, 1),

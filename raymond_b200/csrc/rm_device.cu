@@ -2,6 +2,7 @@
 // wavefront stages (kernels in rm_kernels.cuh), the accumulator, and the device-level C ABI.
 // Citations are relative to the reference checkout (Nyrox/raymond).
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -27,6 +28,78 @@ static int sm_count(int device) {
     return n > 0 ? n : 148;
 }
 
+// ---- device memory: stream-ordered allocations from the device's default pool with the release threshold lifted,
+// so the multi-GB wavefront queues of one render are handed to the next one instead of being unmapped and
+// re-mapped (cudaFree / cudaMalloc of 10 GB cost 0.1-0.5 s each).  All pool traffic is ordered on the legacy
+// default stream; users synchronise their own stream before dev_free().
+static cudaError_t dev_malloc_raw(void** p, size_t bytes) {
+    static std::mutex mu;
+    static std::vector<int> ready;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (std::find(ready.begin(), ready.end(), dev) == ready.end()) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            ready.push_back(dev);
+        }
+    }
+    cudaError_t e = cudaMallocAsync(p, std::max<size_t>(bytes, 32), 0);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    return e;
+}
+template <typename T>
+static cudaError_t dev_malloc(T** p, size_t bytes) { return dev_malloc_raw((void**)p, bytes); }
+static void dev_free(void* p) { if (p) cudaFreeAsync(p, 0); }
+
+// ---- pinned staging pool
+namespace {
+struct PinnedBlock { void* p; size_t bytes; };
+std::mutex g_pin_mu;
+std::vector<PinnedBlock> g_pin_free, g_pin_busy;
+constexpr size_t kPinnedCacheLimit = (size_t)2 << 30;      // blocks beyond 2 GiB of cache are unpinned on release
+}  // namespace
+
+void* pinned_acquire(size_t bytes) {
+    bytes = std::max<size_t>(bytes, 4096);
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    size_t best = g_pin_free.size();
+    for (size_t i = 0; i < g_pin_free.size(); i++)
+        if (g_pin_free[i].bytes >= bytes && (best == g_pin_free.size() || g_pin_free[i].bytes < g_pin_free[best].bytes)) best = i;
+    PinnedBlock b{nullptr, 0};
+    if (best != g_pin_free.size()) {
+        b = g_pin_free[best];
+        g_pin_free.erase(g_pin_free.begin() + (long)best);
+    } else {
+        // drop cached blocks that are too small before pinning a bigger one
+        for (PinnedBlock& f : g_pin_free) cudaFreeHost(f.p);
+        g_pin_free.clear();
+        if (cudaMallocHost(&b.p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        b.bytes = bytes;
+    }
+    g_pin_busy.push_back(b);
+    return b.p;
+}
+
+void pinned_release(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    for (size_t i = 0; i < g_pin_busy.size(); i++)
+        if (g_pin_busy[i].p == p) {
+            PinnedBlock b = g_pin_busy[i];
+            g_pin_busy.erase(g_pin_busy.begin() + (long)i);
+            size_t cached = 0;
+            for (const PinnedBlock& f : g_pin_free) cached += f.bytes;
+            if (cached + b.bytes <= kPinnedCacheLimit) g_pin_free.push_back(b);
+            else cudaFreeHost(b.p);
+            return;
+        }
+}
+
 static DevCamera make_camera(const rm_camera_settings& c) {
     DevCamera d{};
     d.pos[0] = c.position.x; d.pos[1] = c.position.y; d.pos[2] = c.position.z;
@@ -49,14 +122,14 @@ struct IntersectBuffers {
     size_t cap = 0;
     int alloc(size_t n) {
         cap = std::max<size_t>(n, 32);
-        RM_CUDA(cudaMalloc(&hit.t, cap * sizeof(double)));
-        RM_CUDA(cudaMalloc(&hit.obj, cap * sizeof(int)));
-        RM_CUDA(cudaMalloc(&hit.sub, cap * sizeof(unsigned)));
-        RM_CUDA(cudaMalloc(&trav, cap * kTravDoubles * sizeof(double)));
+        RM_CUDA(dev_malloc(&hit.t, cap * sizeof(double)));
+        RM_CUDA(dev_malloc(&hit.obj, cap * sizeof(int)));
+        RM_CUDA(dev_malloc(&hit.sub, cap * sizeof(unsigned)));
+        RM_CUDA(dev_malloc(&trav, cap * kTravDoubles * sizeof(double)));
         return RM_OK;
     }
     void release() {
-        cudaFree(hit.t); cudaFree(hit.obj); cudaFree(hit.sub); cudaFree(trav);
+        dev_free(hit.t); dev_free(hit.obj); dev_free(hit.sub); dev_free(trav);
         hit = HitArrays{}; trav = nullptr; cap = 0;
     }
 };
@@ -83,40 +156,17 @@ struct rm_device_scene {
     unsigned* query_counters = nullptr;     // {traversal records, traversal cursor}
     ~rm_device_scene() {
         cudaSetDevice(device);
-        for (void* p : allocations) cudaFree(p);
+        cudaDeviceSynchronize();            // queries may still be running on the caller's streams
+        for (void* p : allocations) dev_free(p);
         query.release();
-        cudaFree(query_counters);
+        dev_free(query_counters);
     }
 };
 
 namespace rm {
 
-// Page-locked staging buffer: the flattened arrays are written straight into pinned memory and
-// copied H2D from there.
-template <typename T>
-struct Pinned {
-    T* p = nullptr;
-    size_t n = 0;
-    int alloc(size_t count) {
-        n = count;
-        RM_CUDA(cudaMallocHost((void**)&p, std::max<size_t>(count * sizeof(T), 32)));
-        return RM_OK;
-    }
-    ~Pinned() { if (p) cudaFreeHost(p); }
-};
-
-template <typename T>
-static int upload(rm_device_scene* ds, const Pinned<T>& host, const T** out) {
-    void* p = nullptr;
-    size_t bytes = std::max<size_t>(host.n * sizeof(T), 32);
-    RM_CUDA(cudaMalloc(&p, bytes));
-    ds->allocations.push_back(p);
-    ds->bytes += bytes;
-    if (host.n) RM_CUDA(cudaMemcpyAsync(p, host.p, host.n * sizeof(T), cudaMemcpyHostToDevice, 0));
-    *out = (const T*)p;
-    return RM_OK;
-}
-
+// One device allocation + one H2D copy per grid: the flattened arrays are written straight into ONE pinned
+// staging block (cached across calls) laid out like the device block, by a few host threads.
 static int upload_grid(rm_device_scene* ds, const Grid& g, DevGrid* out) {
     DevGrid d{};
     d.bmin[0] = g.bounds.min.x; d.bmin[1] = g.bounds.min.y; d.bmin[2] = g.bounds.min.z;
@@ -126,38 +176,73 @@ static int upload_grid(rm_device_scene* ds, const Grid& g, DevGrid* out) {
     const double ex = d.bmax[0] - d.bmin[0], ey = d.bmax[1] - d.bmin[1], ez = d.bmax[2] - d.bmin[2];
     d.diag2 = ex * ex + ey * ey + ez * ez;
     d.n_cells = g.n_cells();
-    const size_t nc = (size_t)d.n_cells, nt = g.triangles.size();
-    Pinned<uint2> cells;
-    Pinned<unsigned> refs, occ;
-    Pinned<double> tri, nrm;
+    const size_t nc = (size_t)d.n_cells, nt = g.triangles.size(), nr = g.references.size();
     const size_t n_occ = (nc + 31) / 32;
-    if (int st = cells.alloc(nc)) return st;
-    if (int st = occ.alloc(n_occ)) return st;
-    if (int st = refs.alloc(g.references.size())) return st;
-    if (int st = tri.alloc(nt * 12)) return st;
-    if (int st = nrm.alloc(nt * 9)) return st;
-    memset(occ.p, 0, n_occ * sizeof(unsigned));
-    for (size_t c = 0; c < nc; c++) {
-        const unsigned count = g.cell_start[c + 1] - g.cell_start[c];
-        cells.p[c] = make_uint2(g.cell_start[c], count);
-        if (count) occ.p[c >> 5] |= 1u << (c & 31);
-    }
-    if (!g.references.empty()) memcpy(refs.p, g.references.data(), g.references.size() * sizeof(unsigned));
-    for (size_t i = 0; i < nt; i++) {
-        const rm_triangle& t = g.triangles[i];
-        const rm_vertex* v[3] = {&t.v0, &t.v1, &t.v2};
-        for (int k = 0; k < 3; k++) {
-            tri.p[i * 12 + 3 * k + 0] = v[k]->position.x; tri.p[i * 12 + 3 * k + 1] = v[k]->position.y; tri.p[i * 12 + 3 * k + 2] = v[k]->position.z;
-            nrm.p[i * 9 + 3 * k + 0] = v[k]->normal.x; nrm.p[i * 9 + 3 * k + 1] = v[k]->normal.y; nrm.p[i * 9 + 3 * k + 2] = v[k]->normal.z;
+    auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t off_tri = 0, off_shd = off_tri + pad(nt * 12 * sizeof(double)), off_cells = off_shd + pad(nt * 18 * sizeof(double)),
+                 off_occ = off_cells + pad(nc * sizeof(uint2)), off_refs = off_occ + pad(n_occ * sizeof(unsigned)),
+                 total = off_refs + pad(nr * sizeof(unsigned)) + 256;
+    char* host = (char*)pinned_acquire(total);
+    if (!host) return fail(RM_ERR_OUT_OF_MEMORY, "cannot pin " + std::to_string(total) + " bytes of host staging memory");
+    double* tri = (double*)(host + off_tri);
+    double* shd = (double*)(host + off_shd);
+    uint2* cells = (uint2*)(host + off_cells);
+    unsigned* occ = (unsigned*)(host + off_occ);
+    unsigned* refs = (unsigned*)(host + off_refs);
+
+    auto fill_triangles = [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) {
+            const rm_triangle& t = g.triangles[i];
+            const rm_vertex* v[3] = {&t.v0, &t.v1, &t.v2};
+            double* tp = tri + i * 12;
+            double* sp = shd + i * 18;
+            for (int k = 0; k < 3; k++) {
+                tp[3 * k + 0] = v[k]->position.x; tp[3 * k + 1] = v[k]->position.y; tp[3 * k + 2] = v[k]->position.z;
+                sp[3 * k + 0] = v[k]->position.x; sp[3 * k + 1] = v[k]->position.y; sp[3 * k + 2] = v[k]->position.z;
+                sp[9 + 3 * k + 0] = v[k]->normal.x; sp[9 + 3 * k + 1] = v[k]->normal.y; sp[9 + 3 * k + 2] = v[k]->normal.z;
+            }
+            tp[9] = tp[10] = tp[11] = 0.0;
         }
-        tri.p[i * 12 + 9] = tri.p[i * 12 + 10] = tri.p[i * 12 + 11] = 0.0;
+    };
+    auto fill_cells = [&](size_t lo, size_t hi) {      // lo, hi multiples of 32 (whole occupancy words)
+        for (size_t w = lo / 32; w < (hi + 31) / 32; w++) {
+            unsigned bits = 0;
+            for (size_t c = w * 32; c < std::min(w * 32 + 32, nc); c++) {
+                const unsigned count = g.cell_start[c + 1] - g.cell_start[c];
+                cells[c] = make_uint2(g.cell_start[c], count);
+                if (count) bits |= 1u << (c & 31);
+            }
+            occ[w] = bits;
+        }
+    };
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t workers = (nt + nc + nr < ((size_t)1 << 18)) ? 1 : std::min<size_t>(hw ? hw : 4, 8);
+    std::vector<std::thread> pool;
+    for (size_t w = 1; w < workers; w++)
+        pool.emplace_back([&, w] {
+            fill_triangles(nt * w / workers, nt * (w + 1) / workers);
+            fill_cells((nc * w / workers) & ~(size_t)31, w + 1 == workers ? nc : (nc * (w + 1) / workers) & ~(size_t)31);
+        });
+    fill_triangles(0, nt / workers);
+    fill_cells(0, workers == 1 ? nc : (nc / workers) & ~(size_t)31);
+    if (nr) memcpy(refs, g.references.data(), nr * sizeof(unsigned));
+    for (std::thread& t : pool) t.join();
+
+    void* dev = nullptr;
+    cudaError_t e = dev_malloc(&dev, total);
+    if (e == cudaSuccess) {
+        ds->allocations.push_back(dev);
+        ds->bytes += total;
+        e = cudaMemcpyAsync(dev, host, total, cudaMemcpyHostToDevice, 0);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(0);      // the staging block goes back to the pool on return
     }
-    if (int st = upload(ds, cells, &d.cells)) return st;
-    if (int st = upload(ds, occ, &d.occ)) return st;
-    if (int st = upload(ds, refs, &d.refs)) return st;
-    if (int st = upload(ds, tri, &d.tri)) return st;
-    if (int st = upload(ds, nrm, &d.nrm)) return st;
-    RM_CUDA(cudaStreamSynchronize(0));   // the pinned staging buffers are freed on return
+    pinned_release(host);
+    if (e != cudaSuccess) return fail(RM_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(e));
+    d.tri = (const double*)((char*)dev + off_tri);
+    d.shd = (const double*)((char*)dev + off_shd);
+    d.cells = (const uint2*)((char*)dev + off_cells);
+    d.occ = (const unsigned*)((char*)dev + off_occ);
+    d.refs = (const unsigned*)((char*)dev + off_refs);
     *out = d;
     return RM_OK;
 }
@@ -302,9 +387,9 @@ struct rm_renderer {
         for (auto& p : pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
         for (auto& e : stage_pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
         for (auto& e : event_pool) cudaEventDestroy(e);
-        cudaFree(queue_mem); cudaFree(id_mem); cudaFree(pixel_map); cudaFree(rp.contrib); cudaFree(counters); cudaFree(totals);
+        dev_free(queue_mem); dev_free(id_mem); dev_free(pixel_map); dev_free(rp.contrib); dev_free(counters); dev_free(totals);
         isect.release();
-        if (owns_accum) cudaFree(accum);
+        if (owns_accum) dev_free(accum);
         if (owns_stream && stream) cudaStreamDestroy(stream);
         if (owns_scene) delete ds;
     }
@@ -347,23 +432,29 @@ static int renderer_init(rm_renderer* r) {
 
     std::vector<unsigned> map = build_pixel_map(s, r->opt);
     const size_t npix = map.size();
-    RM_CUDA(cudaMalloc(&r->pixel_map, std::max<size_t>(npix, 1) * sizeof(unsigned)));
+    RM_CUDA(dev_malloc(&r->pixel_map, std::max<size_t>(npix, 1) * sizeof(unsigned)));
     if (npix) RM_CUDA(cudaMemcpyAsync(r->pixel_map, map.data(), npix * sizeof(unsigned), cudaMemcpyHostToDevice, r->stream));
     RM_CUDA(cudaStreamSynchronize(r->stream));
 
     // batch: enough paths in flight to fill the machine many times over, bounded in memory
     size_t spp = r->opt.batch_spp;
     if (spp == 0) {
-        const size_t target = (size_t)8 << 20;   // ~8 Mi paths per wavefront batch
+        // ~32 Mi paths per wavefront batch: the deep stages of a batch hold few rays, and every stage ends with the tail
+        // of a persistent kernel, so bigger batches amortise both (measured: 4 -> 16 spp at 1080p is +9 %).  328 B of
+        // queues per path; never more than a quarter of the free device memory.
+        size_t target = (size_t)32 << 20;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) target = std::min(target, std::max<size_t>(free_b / 4 / 328, (size_t)1 << 20));
         spp = npix ? std::max<size_t>(1, target / npix) : 1;
         spp = std::min<size_t>(spp, 64);
+        spp = std::min<size_t>(spp, std::max<size_t>(s.sample_count, 1));
     }
     while (spp > 1 && spp * npix >= 0xffffffffull) spp--;
     r->batch_spp = spp;
     const size_t cap = std::max<size_t>(npix * spp, 32);
 
-    RM_CUDA(cudaMalloc(&r->queue_mem, cap * 9 * 2 * sizeof(double)));
-    RM_CUDA(cudaMalloc(&r->id_mem, cap * 2 * sizeof(unsigned)));
+    RM_CUDA(dev_malloc(&r->queue_mem, cap * 9 * 2 * sizeof(double)));
+    RM_CUDA(dev_malloc(&r->id_mem, cap * 2 * sizeof(unsigned)));
     for (int b = 0; b < 2; b++) {
         for (int k = 0; k < 9; k++) r->q[b].f[k] = r->queue_mem + ((size_t)b * 9 + k) * cap;
         r->q[b].id = r->id_mem + (size_t)b * cap;
@@ -376,17 +467,17 @@ static int renderer_init(rm_renderer* r) {
     rp.n_pixels = (unsigned)npix;
     rp.bounce_limit = (unsigned)s.bounce_limit;
     rp.cap = (unsigned)cap;
-    RM_CUDA(cudaMalloc(&rp.contrib, cap * 3 * sizeof(double)));
+    RM_CUDA(dev_malloc(&rp.contrib, cap * 3 * sizeof(double)));
     r->counter_slots = s.bounce_limit + 2;
-    RM_CUDA(cudaMalloc(&r->counters, r->counter_slots * 3 * sizeof(unsigned)));
+    RM_CUDA(dev_malloc(&r->counters, r->counter_slots * 3 * sizeof(unsigned)));
     rp.cnt.rays = r->counters;
     rp.cnt.trav = r->counters + r->counter_slots;
     rp.cnt.cursor = r->counters + 2 * r->counter_slots;
-    RM_CUDA(cudaMalloc(&r->totals, sizeof(DevTotals)));
+    RM_CUDA(dev_malloc(&r->totals, sizeof(DevTotals)));
     rp.totals = r->totals;
     RM_CUDA(cudaMemsetAsync(r->totals, 0, sizeof(DevTotals), r->stream));
     if (r->opt.accum_device) r->accum = (double*)r->opt.accum_device;
-    else { RM_CUDA(cudaMalloc(&r->accum, W * H * 3 * sizeof(double))); r->owns_accum = true; }
+    else { RM_CUDA(dev_malloc(&r->accum, W * H * 3 * sizeof(double))); r->owns_accum = true; }
     RM_CUDA(cudaMemsetAsync(r->accum, 0, W * H * 3 * sizeof(double), r->stream));
     return RM_OK;
 }
@@ -518,7 +609,7 @@ int rm_device_scene_intersect(rm_device_scene* ds, const rm_ray* rays, size_t co
         ds->query.release();
         if (int st = ds->query.alloc(count)) return st;
     }
-    if (!ds->query_counters) RM_CUDA(cudaMalloc(&ds->query_counters, 2 * sizeof(unsigned)));
+    if (!ds->query_counters) RM_CUDA(dev_malloc(&ds->query_counters, 2 * sizeof(unsigned)));
     RM_CUDA(cudaMemsetAsync(ds->query_counters, 0, 2 * sizeof(unsigned), stream));
     RenderParams rp{};
     SetupArgs sa{};
@@ -552,13 +643,13 @@ int rm_scene_intersect(const rm_scene* scene, int device, const rm_ray* rays, si
     if (!ds) return RM_ERR_CUDA;
     int st = RM_OK;
     rm_ray* d_rays = nullptr; int64_t* d_obj = nullptr; uint64_t* d_sub = nullptr; double* d_t = nullptr;
-    auto cleanup = [&]() { cudaFree(d_rays); cudaFree(d_obj); cudaFree(d_sub); cudaFree(d_t); delete ds; };
+    auto cleanup = [&]() { dev_free(d_rays); dev_free(d_obj); dev_free(d_sub); dev_free(d_t); delete ds; };
 #define RM_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { st = fail(RM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); cleanup(); return st; } } while (0)
     if (count) {
-        RM_TRY(cudaMalloc(&d_rays, count * sizeof(rm_ray)));
-        RM_TRY(cudaMalloc(&d_obj, count * sizeof(int64_t)));
-        RM_TRY(cudaMalloc(&d_sub, count * sizeof(uint64_t)));
-        RM_TRY(cudaMalloc(&d_t, count * sizeof(double)));
+        RM_TRY(dev_malloc(&d_rays, count * sizeof(rm_ray)));
+        RM_TRY(dev_malloc(&d_obj, count * sizeof(int64_t)));
+        RM_TRY(dev_malloc(&d_sub, count * sizeof(uint64_t)));
+        RM_TRY(dev_malloc(&d_t, count * sizeof(double)));
         RM_TRY(cudaMemcpy(d_rays, rays, count * sizeof(rm_ray), cudaMemcpyHostToDevice));
         if (distance) RM_TRY(cudaMemcpy(d_t, distance, count * sizeof(double), cudaMemcpyHostToDevice));   // misses leave it untouched
         st = rm_device_scene_intersect(ds, d_rays, count, d_obj, d_sub, d_t, nullptr);

@@ -56,6 +56,11 @@ struct TileRect { size_t left, top, width, height; };
 // tile split of render_tiled                               src/trace.rs:142-173
 std::vector<TileRect> tile_layout(size_t W, size_t H, size_t tw, size_t th);
 
+// Page-locked host staging blocks, cached across calls (pinning is the expensive part of a short upload).
+// Defined in rm_device.cu.  acquire() returns nullptr when pinning fails.
+void* pinned_acquire(size_t bytes);
+void pinned_release(void* p);
+
 }  // namespace rm
 
 struct rm_mesh { rm::Mesh mesh; };

@@ -35,7 +35,7 @@ constexpr int kBlock = 256;
 //   cells : {first reference, count} per cell            (8 B, one 64-bit load per visited cell)
 //   refs  : triangle indices, ascending inside a cell     (4 B per reference)
 //   tri   : 96 B per triangle, 32 B aligned, 3 sectors: [v0.xyz v1.x][v1.yz v2.xy][v2.z 0 0 0]
-//   nrm   : 72 B per triangle (n0, n1, n2), read once per shaded hit
+//   shd   : 144 B per triangle (v0 v1 v2 n0 n1 n2), read once per shaded hit
 //   occ   : 1 bit per cell, set when the cell holds any reference — 64x smaller than `cells`, so the walk
 //           through empty cells (most of a ray's cells) is served from L1 instead of one L2 trip per cell
 struct DevGrid {
@@ -48,7 +48,7 @@ struct DevGrid {
     const unsigned* occ;
     const unsigned* refs;
     const double* tri;
-    const double* nrm;
+    const double* shd;
 };
 
 struct DevObject {
@@ -375,10 +375,9 @@ __device__ __forceinline__ double heron(D3 a, D3 b, D3 c) {
     return sqrt(s * (s - ab) * (s - ac) * (s - bc));
 }
 __device__ __forceinline__ D3 triangle_normal(const DevGrid& g, unsigned ti, D3 p) {
-    const double* tp = g.tri + (size_t)ti * 12;
+    const double* tp = g.shd + (size_t)ti * 18;
     const D3 v0 = ld3(tp), v1 = ld3(tp + 3), v2 = ld3(tp + 6);
-    const double* np = g.nrm + (size_t)ti * 9;
-    const D3 n0 = ld3(np), n1 = ld3(np + 3), n2 = ld3(np + 6);
+    const D3 n0 = ld3(tp + 9), n1 = ld3(tp + 12), n2 = ld3(tp + 15);
     const double abc = heron(v0, v1, v2);
     const double abp = heron(v0, v1, p);
     const double bcp = heron(v0, v2, p);

@@ -38,7 +38,7 @@ bool make_tile(const TileRect& r, size_t sample_count, const rm_vec3* frame_sums
     return true;
 }
 
-void post_tiles(rm_task* t, uint32_t kind, size_t sample_count, const std::vector<rm_vec3>& sums) {
+void post_tiles(rm_task* t, uint32_t kind, size_t sample_count, const rm_vec3* sums) {
     const size_t W = t->settings.camera_settings.backbuffer_width, H = t->settings.camera_settings.backbuffer_height;
     std::vector<TileRect> tiles = tile_layout(W, H, t->settings.tile_size[0], t->settings.tile_size[1]);
     const int world = t->options.world_size > 1 ? t->options.world_size : 1;
@@ -47,7 +47,7 @@ void post_tiles(rm_task* t, uint32_t kind, size_t sample_count, const std::vecto
         if (t->options.partition == RM_PARTITION_TILES && (int)(i % (size_t)world) != t->options.rank) continue;
         rm_message m{};
         m.kind = kind;
-        if (!make_tile(tiles[i], sample_count, sums.data(), W, &m.tile)) continue;
+        if (!make_tile(tiles[i], sample_count, sums, W, &m.tile)) continue;
         batch.push_back(m);
     }
     std::lock_guard<std::mutex> lk(t->mu);
@@ -65,9 +65,10 @@ void drive(rm_task* t) {
     const size_t stride = split_samples ? world : 1;
     const size_t total = split_samples ? (s.sample_count > first ? (s.sample_count - first + world - 1) / world : 0) : s.sample_count;
     int st = RM_OK;
-    std::vector<rm_vec3> sums;
+    // the frame of running sums lands in a pinned block (cached across tasks): D2H at link speed
+    rm_vec3* sums = (rm_vec3*)pinned_acquire(std::max<size_t>(W * H, 1) * sizeof(rm_vec3));
     try {
-        sums.resize(W * H);
+        if (!sums) throw std::bad_alloc();
         // TileProgressed every `samples_per_iteration` passes (src/trace.rs:217-219)
         const size_t chunk = s.samples_per_iteration ? s.samples_per_iteration : (total ? total : 1);
         size_t done = 0;
@@ -76,15 +77,16 @@ void drive(rm_task* t) {
             st = rm_renderer_render(t->renderer, first + done * stride, n, stride);
             done += n;
             if (st == RM_OK && done < total) {
-                st = rm_renderer_read_sums(t->renderer, sums.data());
+                st = rm_renderer_read_sums(t->renderer, sums);
                 if (st == RM_OK) post_tiles(t, RM_TILE_PROGRESSED, done, sums);
             }
         }
-        if (st == RM_OK) st = rm_renderer_read_sums(t->renderer, sums.data());
+        if (st == RM_OK) st = rm_renderer_read_sums(t->renderer, sums);
         if (st == RM_OK) post_tiles(t, RM_TILE_FINISHED, total, sums);      // src/trace.rs:211-212
     } catch (const std::bad_alloc&) {
         st = fail(RM_ERR_OUT_OF_MEMORY, "out of host memory in the render driver");
     }
+    pinned_release(sums);
     rm_stats stats{};
     rm_renderer_stats(t->renderer, &stats);
     std::lock_guard<std::mutex> lk(t->mu);

@@ -12,7 +12,7 @@ def child(spp):
     from raymond_b200 import api as A, fixtures as F
     sc = A.Scene.from_fixture(F.gold_dragon(F.dragon_standin()))
     st = A.Settings(A.CameraSettings.from_fixture(F.camera(1920, 1080)), spp)
-    r = A.Renderer(sc, st, A.GpuOptions(seed=1))
+    r = A.Renderer(sc, st, A.GpuOptions(seed=1, batch_spp=int(os.environ.get("RM_BATCH_SPP", "0"))))
     r.render(0, 4); r.sync(); r.clear(); r.sync()
     best = 1e9
     for _ in range(3):
@@ -30,6 +30,7 @@ if __name__ == "__main__":
         spp = sys.argv[1] if len(sys.argv) > 1 else "16"
         libs = [os.path.join(ROOT, "raymond_b200", "libraymond_cuda.so")] + sorted(glob.glob(os.path.join(ROOT, "build_variants", "*.so")))
         for lib in libs:
-            env = dict(os.environ, RAYMOND_CUDA_LIB=lib)
-            out = subprocess.run([sys.executable, __file__, "--child", spp], env=env, capture_output=True, text=True)
-            print(f"{os.path.basename(lib):28s} {out.stdout.strip() or out.stderr.strip()[-300:]}", flush=True)
+            for batch in os.environ.get("RM_BATCH_SWEEP", "0").split(","):
+                env = dict(os.environ, RAYMOND_CUDA_LIB=lib, RM_BATCH_SPP=batch)
+                out = subprocess.run([sys.executable, __file__, "--child", spp], env=env, capture_output=True, text=True)
+                print(f"{os.path.basename(lib):28s} batch_spp={batch:3s} {out.stdout.strip() or out.stderr.strip()[-300:]}", flush=True)
