@@ -123,6 +123,10 @@ void rm_mesh_destroy(rm_mesh* mesh);
  * must still be destroyed by the caller.  Returns NULL on failure with
  * rm_last_error() set; `*status` (optional) receives the rm_status. */
 rm_grid* rm_grid_build(rm_mesh* mesh, int* status);
+/* The same AccGrid::build_from_mesh with the cell lists counted, scanned and filled by CUDA kernels on `device`
+ * (identical resolution, cell size and per-cell triangle lists, in the same ascending order, and the same failure
+ * statuses as rm_grid_build).  For meshes of millions of triangles, where the host build takes seconds. */
+rm_grid* rm_grid_build_on_device(rm_mesh* mesh, int device, int* status);
 rm_grid* rm_grid_retain(rm_grid* grid);   /* Arc::clone */
 void rm_grid_release(rm_grid* grid);      /* drop */
 

@@ -122,7 +122,7 @@ TILE_CALLBACK = C.CFUNCTYPE(None, C.POINTER(TileC), C.c_void_p)
 ABI_SYMBOLS = [
     "rm_last_error", "rm_abi_version",
     "rm_mesh_from_triangles", "rm_mesh_load_ply", "rm_mesh_translate", "rm_mesh_triangle_count", "rm_mesh_bounds", "rm_mesh_triangles",
-    "rm_mesh_destroy", "rm_grid_build", "rm_grid_retain", "rm_grid_release", "rm_grid_get_info", "rm_grid_get_cells",
+    "rm_mesh_destroy", "rm_grid_build", "rm_grid_build_on_device", "rm_grid_retain", "rm_grid_release", "rm_grid_get_info", "rm_grid_get_cells",
     "rm_scene_create", "rm_scene_add_sphere", "rm_scene_add_plane", "rm_scene_add_grid", "rm_scene_object_count", "rm_scene_destroy",
     "rm_scene_intersect", "rm_tile_free", "rm_render_tiled", "rm_task_poll", "rm_task_await", "rm_task_set_callback", "rm_task_pump",
     "rm_task_finished", "rm_task_stats", "rm_task_destroy", "rm_device_scene_create", "rm_device_scene_destroy",
@@ -155,6 +155,7 @@ def lib():
         "rm_mesh_triangles": (i32, [vp, sz, sz, vp]),
         "rm_mesh_destroy": (None, [vp]),
         "rm_grid_build": (vp, [vp, P(i32)]),
+        "rm_grid_build_on_device": (vp, [vp, i32, P(i32)]),
         "rm_grid_retain": (vp, [vp]),
         "rm_grid_release": (None, [vp]),
         "rm_grid_get_info": (i32, [vp, P(GridInfoC)]),
@@ -312,10 +313,14 @@ class AccGrid:
         self._h = handle
 
     @classmethod
-    def build_from_mesh(cls, mesh: Mesh) -> "AccGrid":
-        """Consumes the mesh's triangles, like the Rust move."""
+    def build_from_mesh(cls, mesh: Mesh, device: Optional[int] = None) -> "AccGrid":
+        """Consumes the mesh's triangles, like the Rust move.  `device` = CUDA ordinal builds the cell lists on the GPU
+        (same grid, bit for bit); None = the host build."""
         st = C.c_int(0)
-        h = lib().rm_grid_build(mesh._h, C.byref(st))
+        if device is None:
+            h = lib().rm_grid_build(mesh._h, C.byref(st))
+        else:
+            h = lib().rm_grid_build_on_device(mesh._h, int(device), C.byref(st))
         if not h:
             raise RaymondError(st.value, last_error())
         return cls(h)

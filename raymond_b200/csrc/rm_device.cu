@@ -56,12 +56,15 @@ template <typename T>
 static cudaError_t dev_malloc(T** p, size_t bytes) { return dev_malloc_raw((void**)p, bytes); }
 static void dev_free(void* p) { if (p) cudaFreeAsync(p, 0); }
 
+int dev_alloc(void** p, size_t bytes) { return (int)dev_malloc_raw(p, bytes); }
+void dev_release(void* p) { dev_free(p); }
+
 // ---- pinned staging pool
 namespace {
 struct PinnedBlock { void* p; size_t bytes; };
 std::mutex g_pin_mu;
 std::vector<PinnedBlock> g_pin_free, g_pin_busy;
-constexpr size_t kPinnedCacheLimit = (size_t)2 << 30;      // blocks beyond 2 GiB of cache are unpinned on release
+constexpr size_t kPinnedCacheLimit = (size_t)8 << 30;      // blocks beyond 8 GiB of cache are unpinned on release
 }  // namespace
 
 void* pinned_acquire(size_t bytes) {

@@ -63,26 +63,31 @@ static inline bool checked_usize(double v, uint64_t* out) {
 
 struct CellRange { uint64_t lo[3], hi[3]; };
 
-int build_grid(std::vector<rm_triangle>&& tris, const rm_aabb& bounds, std::shared_ptr<Grid>* out) {
-    auto g = std::make_shared<Grid>();
-    const size_t n = tris.size();
-    const double bmin[3] = {bounds.min.x, bounds.min.y, bounds.min.z};
+// estimate_grid_resolution + cell_size                      acc_grid.rs:6-17,38 — shared by the host and the device build
+int grid_dims(const rm_aabb& bounds, size_t n, uint64_t res[3], double cell[3]) {
     const double size[3] = {bounds.max.x - bounds.min.x, bounds.max.y - bounds.min.y, bounds.max.z - bounds.min.z};
-
-    // estimate_grid_resolution                             acc_grid.rs:6-17
     const double volume = std::fabs(size[0] * size[1] * size[2]);
     const double density = std::pow((3.0 * (double)n) / volume, 1.0 / 3.0);
-    uint64_t res[3];
     for (int a = 0; a < 3; a++) res[a] = saturating_usize(std::fabs(size[a]) * density);
     if (res[0] == 0 || res[1] == 0 || res[2] == 0)
         return fail(RM_ERR_DEGENERATE_BOUNDS, "grid resolution has a zero axis (reference: `grid_res[i] - 1` underflows, acc_grid.rs:54)");
-    const double cell[3] = {size[0] / (double)res[0], size[1] / (double)res[1], size[2] / (double)res[2]};
+    for (int a = 0; a < 3; a++) cell[a] = size[a] / (double)res[a];
     if (res[0] > 0x7fffffffull || res[1] > 0x7fffffffull || res[2] > 0x7fffffffull)
         return fail(RM_ERR_UNSUPPORTED, "grid resolution exceeds 2^31 - 1 on an axis");
     const long double cells_ld = (long double)res[0] * (long double)res[1] * (long double)res[2];
     if (cells_ld >= 4294967295.0L) return fail(RM_ERR_UNSUPPORTED, "grid has 2^32 or more cells");
-    const uint64_t n_cells = res[0] * res[1] * res[2];
     if (n >= 0xffffffffull) return fail(RM_ERR_UNSUPPORTED, "mesh has 2^32 or more triangles");
+    return RM_OK;
+}
+
+int build_grid(std::vector<rm_triangle>&& tris, const rm_aabb& bounds, std::shared_ptr<Grid>* out) {
+    auto g = std::make_shared<Grid>();
+    const size_t n = tris.size();
+    const double bmin[3] = {bounds.min.x, bounds.min.y, bounds.min.z};
+    uint64_t res[3];
+    double cell[3];
+    if (int st = grid_dims(bounds, n, res, cell)) return st;
+    const uint64_t n_cells = res[0] * res[1] * res[2];
 
     // pass 1: per-triangle cell range (acc_grid.rs:43-56), per-cell counts
     std::vector<CellRange> ranges(n);
@@ -357,6 +362,28 @@ rm_grid* rm_grid_build(rm_mesh* mesh, int* status) {
             mesh->mesh.triangles.clear();
             mesh->mesh.bounds = mesh_bounds(nullptr, 0);
             st = build_grid(std::move(tris), bounds, &g);
+            if (st == RM_OK) { out = new rm_grid(); out->grid = g; }
+        } catch (const std::bad_alloc&) {
+            st = fail(RM_ERR_OUT_OF_MEMORY, "out of memory while building the grid");
+        }
+    }
+    if (status) *status = st;
+    return out;
+}
+
+rm_grid* rm_grid_build_on_device(rm_mesh* mesh, int device, int* status) {
+    int st = RM_OK;
+    rm_grid* out = nullptr;
+    if (!mesh) {
+        st = fail(RM_ERR_INVALID_ARGUMENT, "rm_grid_build_on_device: null mesh");
+    } else {
+        try {
+            std::shared_ptr<Grid> g;
+            rm_aabb bounds = mesh->mesh.bounds;
+            std::vector<rm_triangle> tris = std::move(mesh->mesh.triangles);   // the Rust call moves the Mesh
+            mesh->mesh.triangles.clear();
+            mesh->mesh.bounds = mesh_bounds(nullptr, 0);
+            st = build_grid_device(std::move(tris), bounds, device, &g);
             if (st == RM_OK) { out = new rm_grid(); out->grid = g; }
         } catch (const std::bad_alloc&) {
             st = fail(RM_ERR_OUT_OF_MEMORY, "out of memory while building the grid");

@@ -39,7 +39,10 @@ struct Grid {
     uint64_t n_cells() const { return resolution[0] * resolution[1] * resolution[2]; }
 };
 // AccGrid::build_from_mesh                                 acc_grid.rs:36-83
+int grid_dims(const rm_aabb& bounds, size_t n, uint64_t res[3], double cell[3]);
 int build_grid(std::vector<rm_triangle>&& tris, const rm_aabb& bounds, std::shared_ptr<Grid>* out);
+// the same, with the cell lists counted, scanned and filled on the GPU (rm_gridbuild.cu)
+int build_grid_device(std::vector<rm_triangle>&& tris, const rm_aabb& bounds, int device, std::shared_ptr<Grid>* out);
 
 enum GeometryKind : int { GEOM_PLANE = 0, GEOM_SPHERE = 1, GEOM_GRID = 2 };   // scene.rs:9-13
 
@@ -60,6 +63,9 @@ std::vector<TileRect> tile_layout(size_t W, size_t H, size_t tw, size_t th);
 // Defined in rm_device.cu.  acquire() returns nullptr when pinning fails.
 void* pinned_acquire(size_t bytes);
 void pinned_release(void* p);
+// Device memory from the cached stream-ordered pool (rm_device.cu); dev_alloc returns a cudaError_t value (0 = ok).
+int dev_alloc(void** p, size_t bytes);
+void dev_release(void* p);
 
 }  // namespace rm
 

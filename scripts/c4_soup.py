@@ -29,6 +29,17 @@ for N in sizes:
         scene = A.Scene.from_fixture(F.soup_scene(tris))
         build_s = time.perf_counter() - t0
         info = scene._grids[0].info()
+        # the same grid built by the CUDA kernels (rm_grid_build_on_device), timed warm
+        dev_build_s, same = None, None
+        for _ in range(2):
+            m = A.Mesh.new(tris)
+            t0 = time.perf_counter()
+            dg = A.AccGrid.build_from_mesh(m, device=0)
+            dev_build_s = time.perf_counter() - t0
+        hs, hr = scene._grids[0].cells()
+        ds_, dr = dg.cells()
+        same = bool(np.array_equal(hs, ds_) and np.array_equal(hr, dr))
+        del dg, m, hs, hr, ds_, dr
         t0 = time.perf_counter()
         ds = A.DeviceScene(scene, 0)
         upload_s = time.perf_counter() - t0
@@ -49,7 +60,7 @@ for N in sizes:
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1))
         line = {"config": "C4 triangle soup", "triangles": N, "box": box_name, "resolution": info["resolution"], "cells": info["cell_count"],
-                "references": info["reference_count"], "host_grid_build_s": round(build_s, 2), "upload_s": round(upload_s, 3), "rays": n,
+                "references": info["reference_count"], "host_grid_build_s": round(build_s, 2), "device_grid_build_s": round(dev_build_s, 3), "device_grid_identical": same, "upload_s": round(upload_s, 3), "rays": n,
                 "ms": best, "mrays_per_s": n / best / 1e3, "hit_fraction": float((obj >= 0).float().mean())}
         if check:
             from oracle import oracle as O
