@@ -48,7 +48,8 @@ typedef enum rm_status {
     RM_ERR_CUDA = -7,
     RM_ERR_UNSUPPORTED = -8,
     RM_ERR_OUT_OF_MEMORY = -9,
-    RM_ERR_STATE = -10
+    RM_ERR_STATE = -10,
+    RM_ERR_PROJECT = -11          /* serde_json::from_reader(file)? fails     project.rs:35   */
 } rm_status;
 
 const char* rm_last_error(void);
@@ -154,6 +155,10 @@ int rm_scene_add_sphere(rm_scene* scene, rm_vec3 origin, double radius, const rm
 int rm_scene_add_plane(rm_scene* scene, rm_vec3 origin, rm_vec3 normal, const rm_material* material);
 /* Geometry::Grid(Arc<AccGrid>) — retains the grid   scene.rs:12 */
 int rm_scene_add_grid(rm_scene* scene, rm_grid* grid, const rm_material* material);
+/* Project::load(path)?.build_scene()             core/src/project.rs:33-57.  The serde_json project file
+ * ({"objects":[{"geometry":{"Sphere"|"Plane"|"Mesh": ..},"material":{"Diffuse"|"Metal"|"Emission": [..]}}]}, externally
+ * tagged enums, cgmath vectors as {"x","y","z"}); a Mesh path is loaded with Mesh::load_ply and built into a grid. */
+rm_scene* rm_project_load_scene(const char* path, int* status);
 size_t rm_scene_object_count(const rm_scene* scene);
 void rm_scene_destroy(rm_scene* scene);
 
@@ -230,6 +235,12 @@ void rm_tile_free(rm_tile* tile);
 typedef enum rm_message_kind { RM_TILE_FINISHED = 0, RM_TILE_PROGRESSED = 1 } rm_message_kind;
 typedef struct rm_message { uint32_t kind; uint32_t reserved; rm_tile tile; } rm_message;
 
+/* The message on the wire (server/src/protocol.rs:9-14: serde tag = "type", content = "data"; Tile per
+ * core/src/tile.rs:6-14): {"type":"TileProgressed","data":{"sample_count":..,"width":..,"height":..,"left":..,"top":..,
+ * "data":[{"x":..,"y":..,"z":..},..]}}.  Returns the length of the JSON text (without the terminator); writes at most
+ * capacity-1 characters + NUL when `buffer` is non-NULL.  Call with NULL to size the buffer. */
+size_t rm_message_to_json(const rm_message* message, char* buffer, size_t capacity);
+
 /* ---------------------------------------------------------- render driver */
 
 typedef struct rm_task rm_task;   /* TaskHandle  src/trace.rs:70-75 */
@@ -298,6 +309,10 @@ int rm_renderer_sync(rm_renderer* r);
 int rm_renderer_read_sums(rm_renderer* r, rm_vec3* out_host);
 /* D2H of sum / sample_count, row-major W*H. */
 int rm_renderer_read_frame(rm_renderer* r, size_t sample_count, rm_vec3* out_host);
+/* The display transform of the reference's front-end (cli_old/src/main.rs:157-181) as an epilogue kernel on the
+ * accumulator: p = sum / sample_count; 1 - exp(p * -1.0 * exposure); powf(1 / gamma); * 255; cast::<u8>() — a pixel
+ * with a NaN / out-of-range channel stays (0, 0, 0).  Writes W*H*3 bytes, row-major RGB, to HOST memory. */
+int rm_renderer_read_rgb8(rm_renderer* r, size_t sample_count, double exposure, double gamma, uint8_t* out_host);
 int rm_renderer_stats(rm_renderer* r, rm_stats* out);
 
 /* Per-stage breakdown of the wavefront.  Slot d (1 <= d < RM_STAGE_SLOTS) is the stage that traces
@@ -320,6 +335,11 @@ typedef struct rm_stage_stats {
 } rm_stage_stats;
 int rm_renderer_stage_stats(rm_renderer* r, rm_stage_stats* out);
 void rm_renderer_destroy(rm_renderer* r);
+
+/* The same display transform for an averaged frame held in HOST memory (what rm_task_await returns). */
+int rm_tonemap_rgb8(const rm_vec3* frame_host, size_t pixels, double exposure, double gamma, int device, uint8_t* out_host);
+/* image.save("output.png")                      cli_old/src/main.rs:194-197: 8-bit RGB PNG (host code). */
+int rm_write_png(const char* path, const uint8_t* rgb8, size_t width, size_t height);
 
 /* Tile rectangles in the reference's queue order (column-major: y advances
  * first, edge tiles clipped — src/trace.rs:142-173).  Returns the tile count;

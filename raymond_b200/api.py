@@ -43,6 +43,7 @@ RM_ERR_DEGENERATE_BOUNDS = -5
 RM_ERR_GRID_CAST = -6
 RM_ERR_CUDA = -7
 RM_ERR_UNSUPPORTED = -8
+RM_ERR_PROJECT = -11
 
 PARTITION_SAMPLES = 0
 PARTITION_TILES = 1
@@ -128,7 +129,8 @@ ABI_SYMBOLS = [
     "rm_task_finished", "rm_task_stats", "rm_task_destroy", "rm_device_scene_create", "rm_device_scene_destroy",
     "rm_device_scene_intersect", "rm_primary_rays_device", "rm_renderer_create", "rm_renderer_create_on", "rm_renderer_render",
     "rm_renderer_accum_device", "rm_renderer_clear", "rm_renderer_sync", "rm_renderer_read_sums", "rm_renderer_read_frame",
-    "rm_renderer_stats", "rm_renderer_stage_stats", "rm_renderer_destroy", "rm_tile_layout",
+    "rm_renderer_stats", "rm_renderer_stage_stats", "rm_renderer_destroy", "rm_tile_layout", "rm_renderer_read_rgb8", "rm_tonemap_rgb8",
+    "rm_write_png", "rm_project_load_scene", "rm_message_to_json",
 ]
 
 _lib = None
@@ -188,6 +190,11 @@ def lib():
         "rm_renderer_sync": (i32, [vp]),
         "rm_renderer_read_sums": (i32, [vp, vp]),
         "rm_renderer_read_frame": (i32, [vp, sz, vp]),
+        "rm_renderer_read_rgb8": (i32, [vp, sz, C.c_double, C.c_double, vp]),
+        "rm_tonemap_rgb8": (i32, [vp, sz, C.c_double, C.c_double, i32, vp]),
+        "rm_write_png": (i32, [C.c_char_p, vp, sz, sz]),
+        "rm_project_load_scene": (vp, [C.c_char_p, P(i32)]),
+        "rm_message_to_json": (sz, [P(MessageC), C.c_char_p, sz]),
         "rm_renderer_stats": (i32, [vp, P(StatsC)]),
         "rm_renderer_stage_stats": (i32, [vp, P(StageStatsC)]),
         "rm_renderer_destroy": (None, [vp]),
@@ -383,6 +390,18 @@ class Scene:
                 raise ValueError(f"unknown object {o[0]!r}")
         return s
 
+    @classmethod
+    def load_project(cls, path: str) -> "Scene":
+        """Project::load(path)?.build_scene() (core/src/project.rs:33-57)."""
+        st = C.c_int(0)
+        h = lib().rm_project_load_scene(os.fsencode(path), C.byref(st))
+        if not h:
+            raise RaymondError(st.value, last_error())
+        s = cls.__new__(cls)
+        s._h = h
+        s._grids = []
+        return s
+
     def __len__(self) -> int:
         return int(lib().rm_scene_object_count(self._h))
 
@@ -496,6 +515,17 @@ class Message:
     tile: Tile
 
 
+def message_to_json(kind: str, tile: Tile) -> str:
+    """The tile message as the reference puts it on the wire (server/src/protocol.rs:9-14)."""
+    data = np.ascontiguousarray(tile.data, dtype=np.float64)
+    m = MessageC(0 if kind == "TileFinished" else 1, 0,
+                 TileC(tile.sample_count, tile.width, tile.height, tile.left, tile.top, C.cast(data.ctypes.data, C.POINTER(Vec3C))))
+    n = lib().rm_message_to_json(C.byref(m), None, 0)
+    buf = C.create_string_buffer(n + 1)
+    lib().rm_message_to_json(C.byref(m), buf, n + 1)
+    return buf.value.decode("ascii")
+
+
 def _tile_from_c(t: TileC) -> Tile:
     n = t.width * t.height
     data = np.ctypeslib.as_array(C.cast(t.data, C.POINTER(C.c_double)), shape=(n * 3,)).copy().reshape(t.height, t.width, 3) if n else np.zeros((0, 0, 3))
@@ -565,6 +595,20 @@ def render_tiled(scene: Scene, settings: Settings, options: Optional[GpuOptions]
     return TaskHandle(h, settings)
 
 
+def tonemap(frame: np.ndarray, exposure: float = 1.0, gamma: float = 2.2, device: int = 0) -> np.ndarray:
+    """cli_old's display transform (cli_old/src/main.rs:157-181) of an averaged (H, W, 3) f64 frame -> uint8, on the GPU."""
+    f = np.ascontiguousarray(frame, dtype=np.float64)
+    out = np.zeros(f.shape, dtype=np.uint8)
+    _check(lib().rm_tonemap_rgb8(_ptr(f), f.size // 3, exposure, gamma, device, _ptr(out)))
+    return out
+
+
+def write_png(path: str, rgb8: np.ndarray) -> None:
+    """image.save(path) (cli_old/src/main.rs:194-197): (H, W, 3) uint8 -> 8-bit RGB PNG."""
+    a = np.ascontiguousarray(rgb8, dtype=np.uint8)
+    _check(lib().rm_write_png(os.fsencode(path), _ptr(a), a.shape[1], a.shape[0]))
+
+
 # ---------------------------------------------------------------------------- device-level interface
 
 class DeviceScene:
@@ -629,6 +673,13 @@ class Renderer:
     def read_frame(self, sample_count: int, out: Optional[np.ndarray] = None) -> np.ndarray:
         out = self._frame() if out is None else out
         _check(lib().rm_renderer_read_frame(self._h, sample_count, _ptr(out)))
+        return out
+
+    def read_rgb8(self, sample_count: int, exposure: float = 1.0, gamma: float = 2.2) -> np.ndarray:
+        """sum / sample_count -> cli_old's tonemap (src cli_old/src/main.rs:157-181) on the GPU -> (H, W, 3) uint8."""
+        cs = self.settings.camera_settings
+        out = np.zeros((cs.backbuffer_height, cs.backbuffer_width, 3), dtype=np.uint8)
+        _check(lib().rm_renderer_read_rgb8(self._h, sample_count, exposure, gamma, _ptr(out)))
         return out
 
     def stats(self) -> dict:

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libraymond_cuda.so")
-SOURCES = ["rm_host.cpp", "rm_task.cpp", "rm_device.cu", "rm_gridbuild.cu"]
+SOURCES = ["rm_host.cpp", "rm_project.cpp", "rm_task.cpp", "rm_device.cu", "rm_gridbuild.cu", "rm_display.cu"]
 HEADERS = ["rm_internal.hpp", "rm_kernels.cuh", os.path.join("..", "..", "include", "raymond.h")]
 
 NVCC_FLAGS = [

@@ -748,6 +748,24 @@ int rm_renderer_read_frame(rm_renderer* r, size_t sample_count, rm_vec3* out) {
     return RM_OK;
 }
 
+int rm_renderer_read_rgb8(rm_renderer* r, size_t sample_count, double exposure, double gamma, uint8_t* out) {
+    if (!r || !out) return fail(RM_ERR_INVALID_ARGUMENT, "rm_renderer_read_rgb8: null argument");
+    RM_CUDA(cudaSetDevice(r->device));
+    const size_t n = r->settings.camera_settings.backbuffer_width * r->settings.camera_settings.backbuffer_height;
+    unsigned char* d_out = nullptr;
+    RM_CUDA(dev_malloc(&d_out, n * 3));
+    // sum / sample_count (src/trace.rs:95), then cli_old/src/main.rs:157-181, on the render stream: 3 B per pixel cross the bus
+    int st = tonemap_device(r->accum, n, (double)sample_count, exposure, gamma, d_out, r->stream);
+    if (st == RM_OK) {
+        r->launches++;
+        if (cudaMemcpyAsync(out, d_out, n * 3, cudaMemcpyDeviceToHost, r->stream) != cudaSuccess || cudaStreamSynchronize(r->stream) != cudaSuccess)
+            st = fail(RM_ERR_CUDA, "D2H of the 8-bit image failed");
+    }
+    dev_free(d_out);
+    harvest_events(r);
+    return st;
+}
+
 int rm_renderer_stats(rm_renderer* r, rm_stats* out) {
     if (!r || !out) return fail(RM_ERR_INVALID_ARGUMENT, "rm_renderer_stats: null argument");
     RM_CUDA(cudaSetDevice(r->device));

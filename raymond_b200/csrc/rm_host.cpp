@@ -207,6 +207,7 @@ rm_vec3 face_tangent(const rm_vertex& x, const rm_vertex& y, const rm_vertex& z)
 
 }  // namespace
 
+int load_ply(const char* path, Mesh* mesh);
 int load_ply(const char* path, Mesh* mesh) {
     std::ifstream f(path, std::ios::binary | std::ios::ate);
     if (!f) return fail(RM_ERR_IO, std::string("cannot read ") + path);
@@ -461,6 +462,72 @@ size_t rm_tile_layout(const rm_settings* s, size_t* rects, size_t capacity) {
         rects[4 * i] = t[i].left; rects[4 * i + 1] = t[i].top; rects[4 * i + 2] = t[i].width; rects[4 * i + 3] = t[i].height;
     }
     return t.size();
+}
+
+// image.save("output.png")                               cli_old/src/main.rs:194-197
+// 8-bit RGB, no interlace, filter 0 on every row, zlib stream of stored (uncompressed) deflate blocks.
+int rm_write_png(const char* path, const uint8_t* rgb8, size_t width, size_t height) {
+    if (!path || (!rgb8 && width * height)) return fail(RM_ERR_INVALID_ARGUMENT, "rm_write_png: null argument");
+    if (width == 0 || height == 0 || width > 0x7fffffffull || height > 0x7fffffffull) return fail(RM_ERR_INVALID_ARGUMENT, "rm_write_png: bad image size");
+    static uint32_t table[256];
+    static bool have_table = false;
+    if (!have_table) {
+        for (uint32_t i = 0; i < 256; i++) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+            table[i] = c;
+        }
+        have_table = true;
+    }
+    auto crc = [&](const uint8_t* p, size_t n, uint32_t c) { for (size_t i = 0; i < n; i++) c = table[(c ^ p[i]) & 0xff] ^ (c >> 8); return c; };
+    auto be32 = [](uint8_t* p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; };
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(RM_ERR_IO, std::string("cannot write ") + path);
+    bool ok = true;
+    auto chunk = [&](const char* type, const uint8_t* data, size_t n) {
+        uint8_t hdr[8];
+        be32(hdr, (uint32_t)n);
+        memcpy(hdr + 4, type, 4);
+        uint32_t c = crc(hdr + 4, 4, 0xffffffffu);
+        c = crc(data, n, c) ^ 0xffffffffu;
+        uint8_t tail[4];
+        be32(tail, c);
+        ok = ok && fwrite(hdr, 1, 8, f) == 8 && (n == 0 || fwrite(data, 1, n, f) == n) && fwrite(tail, 1, 4, f) == 4;
+    };
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    ok = fwrite(sig, 1, 8, f) == 8;
+    uint8_t ihdr[13];
+    be32(ihdr, (uint32_t)width); be32(ihdr + 4, (uint32_t)height);
+    ihdr[8] = 8; ihdr[9] = 2; ihdr[10] = 0; ihdr[11] = 0; ihdr[12] = 0;
+    chunk("IHDR", ihdr, 13);
+    // raw scanlines: filter byte 0 + 3*width bytes
+    const size_t row = 1 + 3 * width, raw_n = row * height;
+    std::vector<uint8_t> z;
+    try {
+        z.reserve(raw_n + raw_n / 65535 * 5 + 16);
+        z.push_back(0x78); z.push_back(0x01);
+        uint32_t a = 1, b = 0;                                  // Adler-32 of the raw data
+        std::vector<uint8_t> raw(raw_n);
+        for (size_t y = 0; y < height; y++) { raw[y * row] = 0; memcpy(&raw[y * row + 1], rgb8 + y * 3 * width, 3 * width); }
+        for (size_t i = 0; i < raw_n; i++) { a = (a + raw[i]) % 65521u; b = (b + a) % 65521u; }
+        for (size_t off = 0; off < raw_n; off += 65535) {
+            const size_t n = std::min<size_t>(65535, raw_n - off);
+            z.push_back(off + n == raw_n ? 1 : 0);
+            z.push_back((uint8_t)(n & 0xff)); z.push_back((uint8_t)(n >> 8));
+            z.push_back((uint8_t)(~n & 0xff)); z.push_back((uint8_t)((~n >> 8) & 0xff));
+            z.insert(z.end(), raw.begin() + (long)off, raw.begin() + (long)(off + n));
+        }
+        uint8_t ad[4];
+        be32(ad, (b << 16) | a);
+        z.insert(z.end(), ad, ad + 4);
+    } catch (const std::bad_alloc&) {
+        fclose(f);
+        return fail(RM_ERR_OUT_OF_MEMORY, "out of memory while encoding the PNG");
+    }
+    chunk("IDAT", z.data(), z.size());
+    chunk("IEND", nullptr, 0);
+    ok = (fclose(f) == 0) && ok;
+    return ok ? RM_OK : fail(RM_ERR_IO, std::string("short write to ") + path);
 }
 
 void rm_tile_free(rm_tile* tile) {

@@ -64,6 +64,8 @@ std::vector<TileRect> tile_layout(size_t W, size_t H, size_t tw, size_t th);
 void* pinned_acquire(size_t bytes);
 void pinned_release(void* p);
 // Device memory from the cached stream-ordered pool (rm_device.cu); dev_alloc returns a cudaError_t value (0 = ok).
+// display transform kernel (rm_display.cu): sums / divisor -> tonemap -> 8-bit RGB, device pointers
+int tonemap_device(const double* sums_device, size_t n_pixels, double divisor, double exposure, double gamma, unsigned char* out_device, void* stream);
 int dev_alloc(void** p, size_t bytes);
 void dev_release(void* p);
 
