@@ -32,9 +32,10 @@ import numpy as np
 METRIC = "Msamples/sec (paths x 5 bounces), GoldDragon 1920x1080 500 spp"
 UNIT = "Msamples/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, from the ncu --set full capture in profiles/ (None = not captured)
-NCU_TRAFFIC = {
-    # profiles/r1_v4_traverse_ncu_summary.md: k_traverse launches of depth 1, 2, 3 of one 4-spp batch read+wrote 0.498 / 1.080 / 0.657 GB
-    "k_traverse": 0.745e9,
+NCU_TRAFFIC_PER_UNIT = {
+    # profiles/r1_v7_traverse_ncu_summary.md: the k_traverse launches of depth 1, 2, 3 of one 8-spp batch (10.4 M grid rays)
+    # read + wrote 1.146 + 2.318 + 1.337 GB of DRAM = 460 B per grid ray
+    "k_traverse": 460.0,
 }
 
 
@@ -328,12 +329,12 @@ def bench_ours(args):
         pk = per_kernel[top]
         ach = pk["bytes"] / (pk["ms"] * 1e-3) / 1e9 if pk["ms"] > 0 else 0.0
         roofline = {"bound": "hbm", "kernel": "k_" + top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": NCU_TRAFFIC.get("k_" + top), "peak_source": peak_src,
+                    "traffic": (NCU_TRAFFIC_PER_UNIT["k_" + top] * pk["units"] / max(pk["launches"], 1)) if "k_" + top in NCU_TRAFFIC_PER_UNIT else None, "peak_source": peak_src,
                     "alg_bytes_per_launch": pk["bytes"] / max(pk["launches"], 1), "alg_bytes_per_unit": pk["bytes"] / max(pk["units"], 1),
                     "unit_name": "grid ray" if top == "traverse" else ("path" if top == "accumulate" else "ray"),
                     "launch_ms_avg": pk["ms"] / max(pk["launches"], 1), "launches": pk["launches"], "share_of_step": pk["ms"] / max(total_ms, 1e-9),
                     "per_kernel_share": {"k_" + k: v["ms"] / max(total_ms, 1e-9) for k, v in per_kernel.items()},
-                    "traffic_note": "ncu dram bytes per launch (depths 1-3 of a 4-spp batch); far BELOW the algorithmic bytes because the "
+                    "traffic_note": "ncu dram bytes per grid ray (460 B, depths 1-3 of an 8-spp batch) x grid rays per launch; far BELOW the algorithmic bytes because the "
                                     "150 MB traversal set is L2-resident and every triangle is fetched by many rays (L2 hit 85-89 %)",
                     "note": "f64 no-FMA traversal of an L2-resident grid: the binding limits are instruction issue (ncu: 50-55 % issue-active, "
                             "FP64 pipe 19-21 %, LSU data pipe 59 %) and L2 latency, not HBM (3-7 % of peak); see DESIGN.md section 6 and profiles/"}

@@ -1,0 +1,92 @@
+// cli_old.cpp — the reference's one working front-end (cli_old/src/main.rs:35-198) on top of the C ABI.
+//
+// Builds the GoldDragon scene exactly as cli_old does (scene :45-127, camera/settings :131-150), calls
+// render_tiled + await (:152-153), applies the display transform (:157-181), writes output.png (:194-197) and prints
+// the total time (:183-188).  With no --mesh the scene is ReflectiveSpheres (the blue sphere cli_old has commented
+// out, :56-58).  Compile:  g++ -O2 -std=c++17 -Iinclude examples/cli_old.cpp -Lraymond_b200 -lraymond_cuda -Wl,-rpath,$PWD/raymond_b200 -o cli_old
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "raymond.h"
+
+static rm_material diffuse(double r, double g, double b, double rough) { rm_material m{}; m.kind = RM_MATERIAL_DIFFUSE; m.a = {r, g, b}; m.p0 = rough; return m; }
+static rm_material metal(double r, double g, double b, double rough) { rm_material m{}; m.kind = RM_MATERIAL_METAL; m.a = {r, g, b}; m.p0 = rough; return m; }
+static rm_material emission(double e) { rm_material m{}; m.kind = RM_MATERIAL_EMISSION; m.a = {e, e, e}; m.b = {1, 1, 1}; m.p0 = 0.27; m.p1 = 0.0; return m; }
+
+#define CHECK(call) do { if ((call) != RM_OK) { fprintf(stderr, "%s failed: %s\n", #call, rm_last_error()); return 1; } } while (0)
+
+int main(int argc, char** argv) {
+    size_t height = 340, width = 340 / 9 * 16, spp = 500;        // cli_old/src/main.rs:131-132,145
+    const char* mesh_path = nullptr;
+    const char* out_path = "output.png";
+    unsigned long long seed = 0;
+    for (int i = 1; i < argc; i++) {
+        if (!strcmp(argv[i], "--mesh") && i + 1 < argc) mesh_path = argv[++i];
+        else if (!strcmp(argv[i], "--out") && i + 1 < argc) out_path = argv[++i];
+        else if (!strcmp(argv[i], "--width") && i + 1 < argc) width = strtoull(argv[++i], nullptr, 10);
+        else if (!strcmp(argv[i], "--height") && i + 1 < argc) height = strtoull(argv[++i], nullptr, 10);
+        else if (!strcmp(argv[i], "--spp") && i + 1 < argc) spp = strtoull(argv[++i], nullptr, 10);
+        else if (!strcmp(argv[i], "--seed") && i + 1 < argc) seed = strtoull(argv[++i], nullptr, 10);
+        else { fprintf(stderr, "usage: cli_old [--mesh dragon.ply] [--out output.png] [--width W --height H --spp N --seed S]\n"); return 2; }
+    }
+    const auto now = std::chrono::steady_clock::now();
+
+    rm_scene* scene = rm_scene_create();
+    rm_material m = diffuse(1.0, 0.0, 0.0, 0.02);
+    CHECK(rm_scene_add_sphere(scene, {-1.0, -0.5, 3.5}, 0.5, &m));                           // :48-55
+    if (mesh_path) {
+        rm_mesh* mesh = rm_mesh_load_ply(mesh_path);                                          // :60
+        if (!mesh) { fprintf(stderr, "load_ply: %s\n", rm_last_error()); return 1; }
+        CHECK(rm_mesh_translate(mesh, {0.0, -0.3, 2.9}));                                     // :61
+        int st = RM_OK;
+        rm_grid* grid = rm_grid_build(mesh, &st);                                             // :62 AccGrid::build_from_mesh
+        rm_mesh_destroy(mesh);
+        if (!grid) { fprintf(stderr, "build_from_mesh: %s\n", rm_last_error()); return 1; }
+        m = metal(1.0, 1.0, 0.1, 0.15);
+        CHECK(rm_scene_add_grid(scene, grid, &m));                                            // :70-75
+        rm_grid_release(grid);
+    } else {
+        m = metal(0.05, 0.25, 1.00, 0.01);
+        CHECK(rm_scene_add_sphere(scene, {0.74, -0.25, 3.5}, 0.75, &m));                      // :56-58
+    }
+    m = diffuse(0.75, 0.75, 0.75, 0.5); CHECK(rm_scene_add_plane(scene, {0, -1, 0}, {0, 1, 0}, &m));      // floor      :77-84
+    m = emission(1.5);                  CHECK(rm_scene_add_plane(scene, {0, 2, 0}, {0, -1, 0}, &m));      // ceiling    :85-92
+    m = diffuse(1, 1, 1, 0.4);          CHECK(rm_scene_add_plane(scene, {0, 0, -2}, {0, 0, 1}, &m));      // front wall :93-100
+    m = diffuse(0, 0, 0, 0.9);          CHECK(rm_scene_add_plane(scene, {0, 0, 5}, {0, 0, -1}, &m));      // back wall  :101-108
+    m = diffuse(0, 0, 0, 0.3);          CHECK(rm_scene_add_plane(scene, {-2, 0, 0}, {1, 0, 0}, &m));      // left wall  :109-117
+    m = diffuse(0, 0, 0, 0.3);          CHECK(rm_scene_add_plane(scene, {2, 0, 0}, {-1, 0, 0}, &m));      // right wall :118-126
+
+    rm_settings settings{};                                                                   // :134-150
+    settings.camera_settings.backbuffer_width = width;
+    settings.camera_settings.backbuffer_height = height;
+    settings.camera_settings.fov_vert = 55.0;
+    settings.camera_settings.position = {0, 0, 0};
+    settings.camera_settings.focal_length = 2.5;
+    settings.camera_settings.aperture_radius = 0.0;
+    settings.sample_count = spp;
+    settings.tile_size[0] = 32; settings.tile_size[1] = 32;
+    settings.bounce_limit = 5;
+    settings.worker_count = 0;
+    rm_gpu_options opt{};
+    opt.seed = seed;
+
+    rm_task* task = rm_render_tiled(scene, &settings, &opt);                                  // :152
+    if (!task) { fprintf(stderr, "render_tiled: %s\n", rm_last_error()); return 1; }
+    rm_scene_destroy(scene);                                                                  // the library snapshotted it
+    std::vector<rm_vec3> render(width * height);
+    CHECK(rm_task_await(task, render.data()));                                                // :153
+    rm_stats stats{};
+    rm_task_stats(task, &stats);
+    rm_task_destroy(task);
+
+    std::vector<uint8_t> export_(width * height * 3);
+    CHECK(rm_tonemap_rgb8(render.data(), width * height, 1.0, 2.2, 0, export_.data()));       // :157-181
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - now).count();
+    printf("Finished render.\nTotal render time: %.3fs\nTotal amount of trace calls: %llu\n", secs, (unsigned long long)stats.rays);   // :183-188
+    CHECK(rm_write_png(out_path, export_.data(), width, height));                             // :194-197
+    return 0;
+}
