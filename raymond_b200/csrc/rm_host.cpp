@@ -467,7 +467,7 @@ size_t rm_tile_layout(const rm_settings* s, size_t* rects, size_t capacity) {
 // image.save("output.png")                               cli_old/src/main.rs:194-197
 // 8-bit RGB, no interlace, filter 0 on every row, zlib stream of stored (uncompressed) deflate blocks.
 int rm_write_png(const char* path, const uint8_t* rgb8, size_t width, size_t height) {
-    if (!path || (!rgb8 && width * height)) return fail(RM_ERR_INVALID_ARGUMENT, "rm_write_png: null argument");
+    if (!path || (!rgb8 && width != 0 && height != 0)) return fail(RM_ERR_INVALID_ARGUMENT, "rm_write_png: null argument");
     if (width == 0 || height == 0 || width > 0x7fffffffull || height > 0x7fffffffull) return fail(RM_ERR_INVALID_ARGUMENT, "rm_write_png: bad image size");
     static uint32_t table[256];
     static bool have_table = false;

@@ -30,6 +30,13 @@ namespace rm {
 constexpr int kMaxObjects = 64;   // objects carried in the kernel parameter block (constant bank)
 constexpr int kMaxGrids = 8;
 constexpr int kBlock = 256;
+// resident blocks per SM the register allocation of each kernel is bounded for (tuning: -DRM_..._BLOCKS_PER_SM=n)
+#ifndef RM_SHADE_BLOCKS_PER_SM
+#define RM_SHADE_BLOCKS_PER_SM 4
+#endif
+#ifndef RM_SETUP_BLOCKS_PER_SM
+#define RM_SETUP_BLOCKS_PER_SM 4
+#endif
 
 // One AccGrid resident in HBM.
 //   cells : {first reference, count} per cell            (8 B, one 64-bit load per visited cell)
@@ -415,52 +422,57 @@ __device__ __forceinline__ bool shade(const DevScene& sc, const RenderParams& rp
     philox(rp.seed, pixel, sample, depth, 1u, w);
     const double rb = u52(w[0], w[1]);
     const double prob_d = 0.5 + metal * (0.0 - 0.5);                        // :263
-    D3 wgt, dir;
-    double eps;
-    if (r < prob_d) {
+    // The two lobes of :264-319 share most of their arithmetic (frame around an axis, normalisations, half vector,
+    // one sincos), so only what differs is branched: a warp holds both kinds of sample.  Per path the operations
+    // and their order are the reference's.
+    const bool diffuse_lobe = r < prob_d;
+    const double kTwoPi = 2.0 * 3.14159265358979323846;
+    D3 axis;
+    double s_t, c_t, phi, eps;       // sin / cos of the polar angle, azimuth, ray offset
+    if (diffuse_lobe) {
         // cosine-weighted hemisphere: theta = acos(sqrt(r1)), pdf = sqrt(r1)      :396-406
-        const double ct = sqrt(ra), st = sqrt(1.0 - ra);
-        double sp, cp;
-        sincos(2.0 * 3.14159265358979323846 * rb, &sp, &cp);
-        D3 tg, bt;
-        onb(normal, tg, bt);
-        dir = normalize(mat_mul(tg, normal, bt, d3(st * cp, ct, st * sp)));    // :266
-        const double cos_theta = fmax(dot(normal, dir), 0.0);                   // :275
-        const D3 half = normalize(dir + view);
-        const double fr = pow5(1.0 - fmax(dot(half, view), 0.0));               // :277
-        const D3 fres = f0 + (d3(1.0, 1.0, 1.0) - f0) * fr;
-        const D3 diff = (d3(1.0, 1.0, 1.0) - fres) * (1.0 - metal);
-        wgt = (mul(diff, color) * cos_theta) / (prob_d * ct);                   // :281-282
+        c_t = sqrt(ra); s_t = sqrt(1.0 - ra);
+        phi = kTwoPi * rb;
+        axis = normal;
         eps = 0.00001;                                                          // :269
     } else {
-        const D3 refl = normalize(-view - 2.0 * (-dot(view, normal) * normal)); // :285
+        axis = normalize(-view - 2.0 * (-dot(view, normal) * normal));          // reflect :285
         const double a = rough * rough;
-        const double phi = 2.0 * 3.14159265358979323846 * ra;
+        phi = kTwoPi * ra;
         const double theta = a * sqrt(rb / (1.0 - rb));                         // :291 (used as an angle)
-        double sth, cth, sp, cp;
-        sincos(theta, &sth, &cth);
-        sincos(phi, &sp, &cp);
-        D3 tg, bt;
-        onb(refl, tg, bt);
-        dir = normalize(mat_mul(tg, refl, bt, d3(sth * cp, cth, sth * sp)));    // :295
-        const double cos_theta = dot(normal, dir);                              // :306
-        const D3 light = normalize(dir);
-        const D3 half = normalize(light + view);
-        const double hv = dot(half, view);
-        const D3 F = f0 + (d3(1.0, 1.0, 1.0) - f0) * pow5(1.0 - hv);            // :309
+        sincos(theta, &s_t, &c_t);
+        eps = 0.0001;                                                           // :300
+    }
+    double sp, cp;
+    sincos(phi, &sp, &cp);
+    D3 tg, bt;
+    onb(axis, tg, bt);
+    const D3 dir = normalize(mat_mul(tg, axis, bt, d3(s_t * cp, c_t, s_t * sp)));   // :266 / :295
+    const double ndl = dot(normal, dir);                                        // :275 / :306
+    const D3 light = diffuse_lobe ? dir : normalize(dir);                       // :307 (the specular lobe normalises again)
+    const D3 half = normalize(light + view);                                    // :276 / :308
+    const double hv = dot(half, view);
+    const D3 one = d3(1.0, 1.0, 1.0);
+    D3 wgt;
+    if (diffuse_lobe) {
+        const double cos_theta = fmax(ndl, 0.0);                                // :275
+        const D3 fres = f0 + (one - f0) * pow5(1.0 - fmax(hv, 0.0));            // :277
+        const D3 diff = (one - fres) * (1.0 - metal);
+        wgt = (mul(diff, color) * cos_theta) / (prob_d * c_t);                  // :281-282
+    } else {
+        const D3 F = f0 + (one - f0) * pow5(1.0 - hv);                          // :309
         const double a2 = rough * rough;                                        // ggx_distribution :362-370
         const double nh = dot(normal, half);
         double den = (nh * nh) * (a2 - 1.0) + 1.0;
         den = fmax(3.14159265358979323846 * den * den, 1e-7);
         const double D = a2 / den;
         const double k = (rough * rough) / 8.0;                                 // geometry_smith :372-382
-        const double nv = fmax(dot(normal, view), 0.0), nl = fmax(dot(normal, dir), 0.0);
+        const double nv = fmax(dot(normal, view), 0.0), nl = fmax(ndl, 0.0);
         const double G = (nv / (nv * (1.0 - k) + k)) * (nl / (nl * (1.0 - k) + k));
         const D3 nom = (D * G) * F;
-        const double denom = 4.0 * dot(normal, view) * cos_theta + 0.001;       // :313
+        const double denom = 4.0 * dot(normal, view) * ndl + 0.001;             // :313
         const double pdf = (D * nh) / (4.0 * hv) + 0.0001;                      // :317
-        wgt = (((nom / denom) * cos_theta) / (1.0 - prob_d)) / pdf;
-        eps = 0.0001;                                                           // :300
+        wgt = (((nom / denom) * ndl) / (1.0 - prob_d)) / pdf;
     }
     T = mul(T, wgt);
     if (T.x == 0.0 && T.y == 0.0 && T.z == 0.0) return false;   // nothing downstream can change a zero path value
@@ -487,7 +499,7 @@ struct SetupArgs {
 
 // Stage part 1.  See the header comment.
 template <int SRC>
-__global__ void __launch_bounds__(kBlock) k_setup(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
+__global__ void __launch_bounds__(kBlock, RM_SETUP_BLOCKS_PER_SM) k_setup(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp,
                                                    const __grid_constant__ SetupArgs a) {
     const unsigned n = a.n_ptr ? *a.n_ptr : a.n_direct;
     const unsigned lane = threadIdx.x & 31u;
@@ -758,7 +770,7 @@ __global__ void __launch_bounds__(kBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(cons
 
 // Stage part 3: shade, then deliver radiance or append the next ray (warp-aggregated compaction).
 template <bool FIRST>
-__global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp, const Queue qin,
+__global__ void __launch_bounds__(kBlock, RM_SHADE_BLOCKS_PER_SM) k_shade(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp, const Queue qin,
                                                    const Queue qout, const HitArrays hit, const unsigned depth, const unsigned n_first) {
     const unsigned n = FIRST ? n_first : rp.cnt.rays[depth - 1];
     const unsigned lane = threadIdx.x & 31u;

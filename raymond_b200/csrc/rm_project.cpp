@@ -265,7 +265,7 @@ rm_scene* rm_project_load_scene(const char* path, int* status) {
 }
 
 size_t rm_message_to_json(const rm_message* message, char* buffer, size_t capacity) {
-    if (!message || (!message->tile.data && message->tile.width * message->tile.height)) return 0;
+    if (!message || (!message->tile.data && message->tile.width != 0 && message->tile.height != 0)) return 0;
     try {
         const std::string s = message_json(*message);
         if (buffer && capacity) {
