@@ -30,6 +30,7 @@ namespace rm {
 constexpr int kMaxObjects = 64;   // objects carried in the kernel parameter block (constant bank)
 constexpr int kMaxGrids = 8;
 constexpr int kBlock = 256;
+constexpr unsigned kMacroWords = 4096;   // 16 KB of coarse occupancy bits in shared memory
 // resident blocks per SM the register allocation of each kernel is bounded for (tuning: -DRM_..._BLOCKS_PER_SM=n)
 #ifndef RM_SHADE_BLOCKS_PER_SM
 #define RM_SHADE_BLOCKS_PER_SM 4
@@ -42,6 +43,8 @@ constexpr int kBlock = 256;
 //   cells : {first reference, count} per cell            (8 B, one 64-bit load per visited cell)
 //   refs  : triangle indices, ascending inside a cell     (4 B per reference)
 //   tri   : 96 B per triangle, 32 B aligned, 3 sectors: [v0.xyz v1.x][v1.yz v2.xy][v2.z 0 0 0]
+//   mocc  : the same at the granularity of 2^mshift-cubed blocks of cells, small enough for shared memory (<= 16 KB)
+//   sph   : 32 B per triangle, a bounding sphere: candidates whose ray line provably misses it skip the 96-B fetch and the test
 //   shd   : 144 B per triangle (v0 v1 v2 n0 n1 n2), read once per shaded hit
 //   occ   : 1 bit per cell, set when the cell holds any reference — 64x smaller than `cells`, so the walk
 //           through empty cells (most of a ray's cells) is served from L1 instead of one L2 trip per cell
@@ -53,8 +56,12 @@ struct DevGrid {
     unsigned long long n_cells;
     const uint2* cells;
     const unsigned* occ;
+    const unsigned* mocc;     // coarse occupancy: 1 bit per block of 2^mshift cubed cells, set when any cell of the block is occupied or
+                              // has an index >= cells.len(); at most kMacroWords words, staged in shared memory by k_traverse
+    unsigned mshift, mrx, mry, mwords;
     const unsigned* refs;
     const double* tri;
+    const double* sph;        // 32 B per triangle: centre of the vertices' bounding box + inflated squared radius + guard (see cull_sphere)
     const double* shd;
 };
 
@@ -267,6 +274,40 @@ __device__ __forceinline__ bool dda_step(const DevGrid& g, Dda& s) {
     return true;
 }
 
+// The same step as predicated instructions (what the hot loop of k_traverse runs): three f64 compares choose the
+// axis, then one integer add, one f64 add and one unsigned range check execute under that axis' predicate.
+// sx/sy/sz = the reference's `step` (+1 / -1).  t_max of a ray that leaves the grid is advanced too; it is dead.
+__device__ __forceinline__ bool dda_step_pred(double& tmx, double& tmy, double& tmz, double tdx, double tdy, double tdz, int& cx, int& cy, int& cz,
+                                              int sx, int sy, int sz, unsigned rx, unsigned ry, unsigned rz) {
+    unsigned alive;
+    asm("{\n\t"
+        ".reg .pred xy, xz, yz, px, py, pz, t, out;\n\t"
+        "setp.lt.f64 xy, %0, %1;\n\t"
+        "setp.lt.f64 xz, %0, %2;\n\t"
+        "setp.lt.f64 yz, %1, %2;\n\t"
+        "and.pred px, xy, xz;\n\t"
+        "not.pred t, xy;\n\t"
+        "and.pred py, t, yz;\n\t"
+        "or.pred t, px, py;\n\t"
+        "not.pred pz, t;\n\t"
+        "@px add.s32 %3, %3, %10;\n\t"
+        "@py add.s32 %4, %4, %11;\n\t"
+        "@pz add.s32 %5, %5, %12;\n\t"
+        "@px add.f64 %0, %0, %7;\n\t"
+        "@py add.f64 %1, %1, %8;\n\t"
+        "@pz add.f64 %2, %2, %9;\n\t"
+        "setp.ge.and.u32 out, %3, %13, px;\n\t"
+        "setp.ge.and.u32 t, %4, %14, py;\n\t"
+        "or.pred out, out, t;\n\t"
+        "setp.ge.and.u32 t, %5, %15, pz;\n\t"
+        "or.pred out, out, t;\n\t"
+        "selp.u32 %6, 0, 1, out;\n\t"
+        "}"
+        : "+d"(tmx), "+d"(tmy), "+d"(tmz), "+r"(cx), "+r"(cy), "+r"(cz), "=r"(alive)
+        : "d"(tdx), "d"(tdy), "d"(tdz), "r"(sx), "r"(sy), "r"(sz), "r"(rx), "r"(ry), "r"(rz));
+    return alive != 0u;
+}
+
 // Triangle::intersects (Moller-Trumbore, two-sided, eps 1e-8)     primitives/triangle.rs:11-44
 struct TriPos { double v0x, v0y, v0z, v1x, v1y, v1z, v2x, v2y, v2z; };
 __device__ __forceinline__ TriPos load_triangle(const double* __restrict__ tp) {
@@ -294,6 +335,19 @@ __device__ __forceinline__ bool hit_triangle(const TriPos& p, D3 o, D3 d, double
     if (!(t > 0.00000001)) return false;
     t_out = t;
     return true;
+}
+
+// Conservative pre-test of Triangle::intersects: true = the (infinite) line of the ray stays outside the triangle's bounding
+// sphere by so much that the reference's f64 Moller-Trumbore arithmetic is certain to return None, so the candidate can be
+// dropped without evaluating it.  The sphere record holds the centre c, r2 = (r (1 + 1e-6) + 1e-9 (1 + |c|))^2 and
+// lim = 1e17 r2.  |cross(c - o, d)|^2 > r2 |d|^2  <=>  distance(line, c) > inflated radius.  Rounding of the cross product
+// is <= ~9e-16 |c - o| |d|, covered by the 1e-6 relative inflation whenever |c - o|^2 < lim (else: not culled); the
+// reference's own rounding can move its barycentrics by <= ~1e-9 of an edge, orders of magnitude inside the inflation.
+// NaN anywhere compares false: not culled.
+__device__ __forceinline__ bool cull_sphere(double cx, double cy, double cz, double r2, D3 o, D3 d, double dd) {
+    const D3 oc = d3(cx - o.x, cy - o.y, cz - o.z);
+    const D3 cr = cross(oc, d);
+    return dot(cr, cr) > r2 * dd && dot(oc, oc) * 1e-17 < r2;
 }
 
 // Scene::intersect keeps the first object among equal distances (strict <, scene.rs:61).  Objects are
@@ -599,7 +653,7 @@ struct TraverseArgs {
 // Idle lanes re-fill from the traversal queue in groups.
 constexpr int kTravWarps = kBlock / 32;
 #ifndef RM_TRAV_MAX_STEPS
-#define RM_TRAV_MAX_STEPS 6
+#define RM_TRAV_MAX_STEPS 2
 #endif
 #ifndef RM_TRAV_REFILL_MIN
 #define RM_TRAV_REFILL_MIN 8
@@ -607,7 +661,11 @@ constexpr int kTravWarps = kBlock / 32;
 #ifndef RM_TRAV_BLOCKS_PER_SM
 #define RM_TRAV_BLOCKS_PER_SM 3
 #endif
-constexpr unsigned kTravMaxSteps = RM_TRAV_MAX_STEPS;     // DDA steps per phase A
+#ifndef RM_TRAV_LOOK
+#define RM_TRAV_LOOK 4
+#endif
+constexpr unsigned kLook = RM_TRAV_LOOK;                  // cells looked ahead per walk iteration
+constexpr unsigned kTravMaxSteps = RM_TRAV_MAX_STEPS;     // walk iterations per phase A
 constexpr unsigned kRefillMin = RM_TRAV_REFILL_MIN;       // idle lanes that trigger a re-fill while others still have work
 
 struct TravWarpShared {
@@ -616,14 +674,28 @@ struct TravWarpShared {
     unsigned cand_pos[32];             // ... and the earliest list position that has it
     unsigned prefix[33];               // exclusive prefix of the pooled list lengths
     unsigned kstart[32];               // first reference of the lane's cell
+    double dd[32];                     // |d|^2 of the lane's ray
+    unsigned s_pos[64], s_ti[64];      // ring of candidates that survived the sphere pre-test: list position, triangle
+    unsigned char s_owner[64];         // ... and the lane that owns the ray
 };
 
 enum TravState : unsigned { TS_IDLE = 0, TS_LOOK = 1, TS_STEP = 2, TS_READY = 3 };
 
+#if defined(RM_TRAV_PROFILE)
+// -DRM_TRAV_PROFILE: SM-clock cycles per phase, summed over warps (tuning builds only; read with rm_debug_trav_profile)
+__device__ unsigned long long g_trav_prof[8];
+#define RM_PROF_MARK(slot) do { const long long now__ = clock64(); prof[slot] += (unsigned long long)(now__ - prof_t); prof_t = now__; } while (0)
+#else
+#define RM_PROF_MARK(slot) do { } while (0)
+#endif
+
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(const __grid_constant__ DevGrid g, const __grid_constant__ TraverseArgs a) {
     __shared__ TravWarpShared shared[kTravWarps];
+    __shared__ unsigned macro[kMacroWords];
     TravWarpShared& sh = shared[threadIdx.x >> 5];
+    for (unsigned w = threadIdx.x; w < g.mwords; w += blockDim.x) macro[w] = __ldg(&g.mocc[w]);
+    __syncthreads();
     const unsigned n = *a.n_ptr;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt = (1u << lane) - 1u;
@@ -633,11 +705,21 @@ __global__ void __launch_bounds__(kBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(cons
 
     unsigned state = TS_IDLE;
     bool exhausted = false;                 // the queue has no more records for this warp
-    Dda s{};
+    // DDA state of MY ray (acc_grid.rs:100-125)
+    double tmx = 0, tmy = 0, tmz = 0, tdx = 0, tdy = 0, tdz = 0;
+    int cx = 0, cy = 0, cz = 0, sx = 1, sy = 1, sz = 1;
+    bool inside = false;                    // current_cell lies inside the grid on every axis (stays true once true)
+    const unsigned rx = (unsigned)g.res[0], ry = (unsigned)g.res[1], rz = (unsigned)g.res[2];
+    const unsigned ms = g.mshift, mrx = g.mrx, mry = g.mry;
     unsigned ray = 0, k = 0, cnt = 0;
     unsigned n_cells = 0, n_tests = 0;
+#if defined(RM_TRAV_PROFILE)
+    unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_t = clock64();
+#endif
     for (;;) {
         // ---- re-fill
+        RM_PROF_MARK(4);
         const unsigned idle = __ballot_sync(FULL, state == TS_IDLE);
         if (idle == FULL && exhausted) break;
         if (!exhausted && (idle == FULL || __popc(idle) >= (int)kRefillMin)) {
@@ -649,41 +731,86 @@ __global__ void __launch_bounds__(kBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(cons
                 const unsigned idx = base + __popc(idle & lt);
                 if (idx < n) {
                     const double* rec = a.trav + (size_t)idx * kTravDoubles;
-                    double ox, oy, oz, dx, dy, dz, c0, c1, c2, c3;
+                    double ox, oy, oz, dx, dy, dz, q0, q1, q2, q3;
                     ld256(rec, ox, oy, oz, dx);
-                    ld256(rec + 4, dy, dz, s.tmx, s.tmy);
-                    ld256(rec + 8, s.tmz, s.tdx, s.tdy, s.tdz);
-                    ld256(rec + 12, c0, c1, c2, c3);
-                    s.cx = __double2loint(c0); s.cy = __double2hiint(c0);
-                    s.cz = __double2loint(c1); s.step = (unsigned)__double2hiint(c1);
-                    ray = (unsigned)__double2loint(c2);
+                    ld256(rec + 4, dy, dz, tmx, tmy);
+                    ld256(rec + 8, tmz, tdx, tdy, tdz);
+                    ld256(rec + 12, q0, q1, q2, q3);
+                    cx = __double2loint(q0); cy = __double2hiint(q0); cz = __double2loint(q1);
+                    const unsigned neg = (unsigned)__double2hiint(q1);
+                    sx = (neg & 1u) ? -1 : 1; sy = (neg & 2u) ? -1 : 1; sz = (neg & 4u) ? -1 : 1;
+                    ray = (unsigned)__double2loint(q2);
+                    inside = (unsigned)cx < rx && (unsigned)cy < ry && (unsigned)cz < rz;
                     sh.ray[lane][0] = make_double2(ox, oy);
                     sh.ray[lane][1] = make_double2(oz, dx);
                     sh.ray[lane][2] = make_double2(dy, dz);
+                    sh.dd[lane] = (dx * dx + dy * dy) + dz * dz;
                     state = TS_LOOK;
                 }
             }
         }
-        // ---- A: walk to the next non-empty cell
+        RM_PROF_MARK(0);
+        // ---- A: walk to the next non-empty cell.  The walk is a chain of dependent round trips (step -> occupancy word),
+        // so each iteration looks kLook cells ahead: the DDA is advanced kLook times in registers (the arithmetic is
+        // cheap and exactly the reference's sequence), the kLook occupancy words are fetched together, and the ray
+        // commits up to the first occupied cell (re-walking from the saved state) or all kLook empty ones.
 #pragma unroll 1
         for (unsigned it = 0; it < kTravMaxSteps; it++) {
-            if (state == TS_LOOK || state == TS_STEP) {
+            if (state == TS_LOOK) {                              // a fresh ray: its start cell, no step (acc_grid.rs:127-131)
                 unsigned long long ci;
-                if ((state == TS_LOOK || dda_step(g, s)) && grid_cell_index(g, s.cx, s.cy, s.cz, ci)) {
+                state = TS_IDLE;                                 // index >= cells.len(): the reference returns None
+                if (grid_cell_index(g, cx, cy, cz, ci)) {
                     state = TS_STEP;
                     if (COUNT) n_cells++;
-                    if ((__ldg(&g.occ[ci >> 5]) >> (ci & 31u)) & 1u) {
-                        const uint2 cell = __ldg(&g.cells[ci]);
-                        k = cell.x; cnt = cell.y;
-                        state = TS_READY;
-                        if (COUNT) n_tests += cnt;
+                    if ((__ldg(&g.occ[ci >> 5]) >> (ci & 31u)) & 1u) { k = (unsigned)ci; state = TS_READY; }
+                }
+            } else if (state == TS_STEP) {
+                const double a0 = tmx, a1 = tmy, a2 = tmz;
+                const int b0 = cx, b1 = cy, b2 = cz;
+                unsigned idx[kLook], word[kLook];
+                unsigned ended = kLook;                          // first look-ahead step at which the traversal ends without a cell
+#pragma unroll
+                for (unsigned j = 0; j < kLook; j++) {
+                    idx[j] = 0u; word[j] = 0u;
+                    if (ended == kLook) {
+                        unsigned long long ci;
+                        if (dda_step_pred(tmx, tmy, tmz, tdx, tdy, tdz, cx, cy, cz, sx, sy, sz, rx, ry, rz) && grid_cell_index(g, cx, cy, cz, ci)) {
+                            idx[j] = (unsigned)ci;
+                            word[j] = __ldg(&g.occ[ci >> 5]);
+                        } else {
+                            ended = j;                           // left the grid, or index >= cells.len(): None
+                        }
                     }
+                }
+                unsigned first = kLook;                          // first occupied cell among the ones reached
+#pragma unroll
+                for (unsigned j = kLook; j-- > 0;)
+                    if (j < ended && ((word[j] >> (idx[j] & 31u)) & 1u)) first = j;
+                if (first < kLook) {
+                    // commit first + 1 steps: re-walk from the saved state (same operations, same results)
+                    tmx = a0; tmy = a1; tmz = a2; cx = b0; cy = b1; cz = b2;
+#pragma unroll
+                    for (unsigned j = 0; j < kLook; j++)
+                        if (j <= first) dda_step_pred(tmx, tmy, tmz, tdx, tdy, tdz, cx, cy, cz, sx, sy, sz, rx, ry, rz);
+                    k = idx[0];
+#pragma unroll
+                    for (unsigned j = 1; j < kLook; j++) if (j == first) k = idx[j];
+                    state = TS_READY;
+                    if (COUNT) n_cells += first + 1u;
                 } else {
-                    state = TS_IDLE;        // left the grid / index out of range: the reference returns None
+                    if (COUNT) n_cells += ended;
+                    if (ended < kLook) state = TS_IDLE;          // the reference returns None
                 }
             }
-            if (!__any_sync(FULL, state == TS_LOOK || state == TS_STEP)) break;
+            if (!__any_sync(FULL, state == TS_STEP)) break;
         }
+        // the cell records of every ray that found an occupied cell, in one round trip (not one per walk iteration)
+        if (state == TS_READY) {
+            const uint2 cell = __ldg(&g.cells[k]);
+            k = cell.x; cnt = cell.y;
+            if (COUNT) n_tests += cnt;
+        }
+        RM_PROF_MARK(1);
         // ---- B: pooled triangle tests of every ready cell
         const unsigned mine = state == TS_READY ? cnt : 0u;
         unsigned incl = mine;
@@ -712,18 +839,46 @@ __global__ void __launch_bounds__(kBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(cons
             pos = sh.kstart[lo] + (item - sh.prefix[lo]);
             ti = __ldg(&g.refs[pos]);
         };
+        // Two stages, both with full lanes.  Stage 1: a round of 32 candidates is located, their bounding-sphere records
+        // (32 B) fetched, and the candidates whose ray provably misses are dropped; survivors are appended (ballot
+        // compaction, order kept) to a ring in shared memory.  Stage 2, whenever 32 survivors wait (or the pool is
+        // exhausted): the real Triangle::intersects on the 96-B records.
         unsigned owner = 0, pos = 0, ti = 0;
         if (lane < total) locate(lane, owner, pos, ti);
-        for (unsigned base = 0; base < total; base += 32u) {
-            const bool valid = base + lane < total;
+        unsigned base = 0, q_head = 0, q_count = 0;          // warp-uniform
+        for (;;) {
+            if (base < total && q_count < 32u) {
+                const bool valid = base + lane < total;
+                const unsigned c_owner = owner, c_pos = pos, c_ti = ti;
+                double scx = 0, scy = 0, scz = 0, sr2 = 0;
+                if (valid) ld256_nc(g.sph + (size_t)c_ti * 4, scx, scy, scz, sr2);
+                // the next round's reference is fetched while this round's sphere is in flight
+                if (base + 32u + lane < total) locate(base + 32u + lane, owner, pos, ti);
+                bool pass = false;
+                if (valid) {
+                    const double2 r0 = sh.ray[c_owner][0], r1 = sh.ray[c_owner][1], r2 = sh.ray[c_owner][2];
+                    pass = !cull_sphere(scx, scy, scz, sr2, d3(r0.x, r0.y, r1.x), d3(r1.y, r2.x, r2.y), sh.dd[c_owner]);
+                }
+                const unsigned m = __ballot_sync(FULL, pass);
+                if (pass) {
+                    const unsigned slot = (q_head + q_count + __popc(m & lt)) & 63u;
+                    sh.s_pos[slot] = c_pos; sh.s_ti[slot] = c_ti; sh.s_owner[slot] = (unsigned char)c_owner;
+                }
+                q_count += __popc(m);
+                base += 32u;
+                __syncwarp();
+                continue;
+            }
+            if (q_count == 0u) break;
+            const unsigned take = q_count < 32u ? q_count : 32u;
+            const bool valid = lane < take;
             bool got = false;
             unsigned long long tb = 0;
-            const unsigned c_owner = owner, c_pos = pos;
-            TriPos tp;
-            if (valid) tp = load_triangle(g.tri + (size_t)ti * 12);
-            // the next round's reference is fetched while this round's triangle is in flight
-            if (base + 32u + lane < total) locate(base + 32u + lane, owner, pos, ti);
+            unsigned c_owner = 0, c_pos = 0;
             if (valid) {
+                const unsigned slot = (q_head + lane) & 63u;
+                c_owner = sh.s_owner[slot]; c_pos = sh.s_pos[slot];
+                const TriPos tp = load_triangle(g.tri + (size_t)sh.s_ti[slot] * 12);
                 const double2 r0 = sh.ray[c_owner][0], r1 = sh.ray[c_owner][1], r2 = sh.ray[c_owner][2];
                 double t;
                 if (hit_triangle(tp, d3(r0.x, r0.y, r1.x), d3(r1.y, r2.x, r2.y), t)) {
@@ -732,6 +887,8 @@ __global__ void __launch_bounds__(kBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(cons
                     atomicMin(&sh.cand_t[c_owner], tb);
                 }
             }
+            q_head = (q_head + take) & 63u;
+            q_count -= take;
             if (__any_sync(FULL, got)) {
                 __syncwarp();
                 if (got && sh.cand_t[c_owner] == tb) atomicMin(&sh.cand_pos[c_owner], c_pos);
@@ -741,9 +898,10 @@ __global__ void __launch_bounds__(kBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(cons
                 if (ct < best_t) { best_t = ct; best_pos = sh.cand_pos[lane]; }
                 sh.cand_t[lane] = ~0ull;
                 sh.cand_pos[lane] = ~0u;
-                __syncwarp();
             }
+            __syncwarp();       // the ring slots just read may be rewritten by the next stage-1 round
         }
+        RM_PROF_MARK(2);
         // ---- C
         if (state == TS_READY) {
             if (best_pos != ~0u) {
@@ -758,7 +916,14 @@ __global__ void __launch_bounds__(kBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(cons
             }
         }
         __syncwarp();       // shared rays / prefix are rewritten by the next iteration
+        RM_PROF_MARK(3);
     }
+#if defined(RM_TRAV_PROFILE)
+    if (lane == 0) {
+        for (int i = 0; i < 5; i++) atomicAdd(&g_trav_prof[i], prof[i]);
+        atomicAdd(&g_trav_prof[7], 1ull);
+    }
+#endif
     if (COUNT) {
         const unsigned c = __reduce_add_sync(FULL, n_cells), t = __reduce_add_sync(FULL, n_tests);
         if (lane == 0) {
