@@ -181,30 +181,20 @@ static int upload_grid(rm_device_scene* ds, const Grid& g, DevGrid* out) {
     d.n_cells = g.n_cells();
     const size_t nc = (size_t)d.n_cells, nt = g.triangles.size(), nr = g.references.size();
     const size_t n_occ = (nc + 31) / 32;
-    // coarse occupancy: blocks of 2^mshift cubed cells, the smallest block size (>= 4) whose bitmap fits kMacroWords
-    unsigned mshift = 2;
-    size_t mr[3], mbits;
-    for (;; mshift++) {
-        for (int a = 0; a < 3; a++) mr[a] = ((size_t)d.res[a] + ((size_t)1 << mshift) - 1) >> mshift;
-        mbits = mr[0] * mr[1] * mr[2];
-        if ((mbits + 31) / 32 <= kMacroWords) break;
-    }
-    const size_t n_mocc = (mbits + 31) / 32;
-    d.mshift = mshift; d.mrx = (unsigned)mr[0]; d.mry = (unsigned)mr[1]; d.mwords = (unsigned)n_mocc;
     auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t off_tri = 0, off_sph = off_tri + pad(nt * 12 * sizeof(double)), off_shd = off_sph + pad(nt * 4 * sizeof(double)),
+    const size_t off_tri = 0, off_sph = off_tri + pad(nt * 12 * sizeof(double)), off_shd = off_sph + pad(nr * sizeof(float4)),
                  off_cells = off_shd + pad(nt * 18 * sizeof(double)),
-                 off_occ = off_cells + pad(nc * sizeof(uint2)), off_mocc = off_occ + pad(n_occ * sizeof(unsigned)),
-                 off_refs = off_mocc + pad(n_mocc * sizeof(unsigned)), total = off_refs + pad(nr * sizeof(unsigned)) + 256;
+                 off_occ = off_cells + pad(nc * sizeof(uint2)), off_refs = off_occ + pad(n_occ * sizeof(unsigned)),
+                 total = off_refs + pad(nr * sizeof(unsigned)) + 256;
     char* host = (char*)pinned_acquire(total);
     if (!host) return fail(RM_ERR_OUT_OF_MEMORY, "cannot pin " + std::to_string(total) + " bytes of host staging memory");
     double* tri = (double*)(host + off_tri);
     double* shd = (double*)(host + off_shd);
-    double* sph = (double*)(host + off_sph);
+    float4* sphr = (float4*)(host + off_sph);          // one sphere per REFERENCE, in reference order
+    std::vector<float4> sph_tri(nt);                     // ... copied from one per triangle
     uint2* cells = (uint2*)(host + off_cells);
     unsigned* occ = (unsigned*)(host + off_occ);
     unsigned* refs = (unsigned*)(host + off_refs);
-    unsigned* mocc = (unsigned*)(host + off_mocc);
 
     auto fill_triangles = [&](size_t lo, size_t hi) {
         for (size_t i = lo; i < hi; i++) {
@@ -218,23 +208,25 @@ static int upload_grid(rm_device_scene* ds, const Grid& g, DevGrid* out) {
                 sp[9 + 3 * k + 0] = v[k]->normal.x; sp[9 + 3 * k + 1] = v[k]->normal.y; sp[9 + 3 * k + 2] = v[k]->normal.z;
             }
             tp[9] = tp[10] = tp[11] = 0.0;
-            // bounding sphere for the conservative pre-test (cull_sphere): centre of the vertices' box, radius to the
-            // farthest vertex, inflated; a non-finite triangle gets r2 = +inf (never culled)
-            double c[3], r2 = 0.0, cmax = 0.0;
+            // bounding sphere for the conservative pre-test (cull_sphere): f32 centre near the centre of the vertices' box,
+            // radius to the farthest vertex measured from that f32 centre, inflated and rounded up; a non-finite triangle
+            // gets an infinite radius (never culled)
+            float cf[3];
+            double cmax = 0.0, r2 = 0.0;
             for (int a = 0; a < 3; a++) {
                 const double lo = std::fmin(tp[a], std::fmin(tp[3 + a], tp[6 + a])), hi = std::fmax(tp[a], std::fmax(tp[3 + a], tp[6 + a]));
-                c[a] = 0.5 * (lo + hi);
-                cmax = std::fmax(cmax, std::fabs(c[a]));
+                cf[a] = (float)(0.5 * (lo + hi));
+                cmax = std::fmax(cmax, std::fabs((double)cf[a]));
             }
             for (int k = 0; k < 3; k++) {
-                const double dx = tp[3 * k] - c[0], dy = tp[3 * k + 1] - c[1], dz = tp[3 * k + 2] - c[2];
+                const double dx = tp[3 * k] - (double)cf[0], dy = tp[3 * k + 1] - (double)cf[1], dz = tp[3 * k + 2] - (double)cf[2];
                 r2 = std::fmax(r2, dx * dx + dy * dy + dz * dz);
             }
-            double r = std::sqrt(r2) * (1.0 + 1e-6) + 1e-9 * (1.0 + cmax);
-            double* q = sph + i * 4;
-            q[0] = c[0]; q[1] = c[1]; q[2] = c[2];
-            q[3] = r * r * (1.0 + 1e-12);
-            if (!(q[3] == q[3]) || !std::isfinite(c[0]) || !std::isfinite(c[1]) || !std::isfinite(c[2])) { q[0] = q[1] = q[2] = 0.0; q[3] = INFINITY; }
+            const double r = std::sqrt(r2) * (1.0 + 1e-6) + 1e-9 * (1.0 + cmax);
+            float rf = (float)r;
+            if (!((double)rf >= r)) rf = std::nextafterf(rf, INFINITY);
+            if (!(r == r) || !std::isfinite(cf[0]) || !std::isfinite(cf[1]) || !std::isfinite(cf[2])) { cf[0] = cf[1] = cf[2] = 0.f; rf = INFINITY; }
+            sph_tri[i] = make_float4(cf[0], cf[1], cf[2], rf);
         }
     };
     auto fill_cells = [&](size_t lo, size_t hi) {      // lo, hi multiples of 32 (whole occupancy words)
@@ -260,23 +252,13 @@ static int upload_grid(rm_device_scene* ds, const Grid& g, DevGrid* out) {
     fill_cells(0, workers == 1 ? nc : (nc / workers) & ~(size_t)31);
     if (nr) memcpy(refs, g.references.data(), nr * sizeof(unsigned));
     for (std::thread& t : pool) t.join();
-    // coarse bits from the fine ones, through the reference's index x + res.x * (y + z * res.z) (aliasing included);
-    // a cell whose index is >= cells.len() ends a traversal, so it counts as occupied
-    memset(mocc, 0, n_mocc * sizeof(unsigned));
+    pool.clear();
     {
-        const size_t rx_ = (size_t)d.res[0], ry_ = (size_t)d.res[1], rz_ = (size_t)d.res[2];
-        for (size_t z = 0; z < rz_; z++)
-            for (size_t y = 0; y < ry_; y++) {
-                const size_t row = rx_ * (y + z * rz_);
-                const size_t mrow = mr[0] * ((y >> mshift) + (z >> mshift) * mr[1]);
-                for (size_t x = 0; x < rx_; x++) {
-                    const size_t idx = row + x;
-                    const bool hot = idx >= nc || ((occ[idx >> 5] >> (idx & 31)) & 1u);
-                    if (hot) { const size_t mi = mrow + (x >> mshift); mocc[mi >> 5] |= 1u << (mi & 31); }
-                }
-            }
+        auto spread = [&](size_t lo, size_t hi) { for (size_t p = lo; p < hi; p++) sphr[p] = sph_tri[g.references[p]]; };
+        for (size_t w = 1; w < workers; w++) pool.emplace_back(spread, nr * w / workers, nr * (w + 1) / workers);
+        spread(0, nr / workers);
+        for (std::thread& t : pool) t.join();
     }
-
     void* dev = nullptr;
     cudaError_t e = dev_malloc(&dev, total);
     if (e == cudaSuccess) {
@@ -289,10 +271,9 @@ static int upload_grid(rm_device_scene* ds, const Grid& g, DevGrid* out) {
     if (e != cudaSuccess) return fail(RM_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(e));
     d.tri = (const double*)((char*)dev + off_tri);
     d.shd = (const double*)((char*)dev + off_shd);
-    d.sph = (const double*)((char*)dev + off_sph);
+    d.sphr = (const float4*)((char*)dev + off_sph);
     d.cells = (const uint2*)((char*)dev + off_cells);
     d.occ = (const unsigned*)((char*)dev + off_occ);
-    d.mocc = (const unsigned*)((char*)dev + off_mocc);
     d.refs = (const unsigned*)((char*)dev + off_refs);
     *out = d;
     return RM_OK;

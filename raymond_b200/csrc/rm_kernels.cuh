@@ -30,7 +30,6 @@ namespace rm {
 constexpr int kMaxObjects = 64;   // objects carried in the kernel parameter block (constant bank)
 constexpr int kMaxGrids = 8;
 constexpr int kBlock = 256;
-constexpr unsigned kMacroWords = 4096;   // 16 KB of coarse occupancy bits in shared memory
 // resident blocks per SM the register allocation of each kernel is bounded for (tuning: -DRM_..._BLOCKS_PER_SM=n)
 #ifndef RM_SHADE_BLOCKS_PER_SM
 #define RM_SHADE_BLOCKS_PER_SM 4
@@ -43,8 +42,9 @@ constexpr unsigned kMacroWords = 4096;   // 16 KB of coarse occupancy bits in sh
 //   cells : {first reference, count} per cell            (8 B, one 64-bit load per visited cell)
 //   refs  : triangle indices, ascending inside a cell     (4 B per reference)
 //   tri   : 96 B per triangle, 32 B aligned, 3 sectors: [v0.xyz v1.x][v1.yz v2.xy][v2.z 0 0 0]
-//   mocc  : the same at the granularity of 2^mshift-cubed blocks of cells, small enough for shared memory (<= 16 KB)
-//   sph   : 32 B per triangle, a bounding sphere: candidates whose ray line provably misses it skip the 96-B fetch and the test
+//   sphr  : 16 B per reference (f32 centre + inflated radius of the triangle's bounding sphere), in the order of `refs`, so the
+//           candidates of a cell are one contiguous, coalesced read; candidates whose ray line provably misses the sphere
+//           skip the reference, the 96-B fetch and the test
 //   shd   : 144 B per triangle (v0 v1 v2 n0 n1 n2), read once per shaded hit
 //   occ   : 1 bit per cell, set when the cell holds any reference — 64x smaller than `cells`, so the walk
 //           through empty cells (most of a ray's cells) is served from L1 instead of one L2 trip per cell
@@ -56,12 +56,9 @@ struct DevGrid {
     unsigned long long n_cells;
     const uint2* cells;
     const unsigned* occ;
-    const unsigned* mocc;     // coarse occupancy: 1 bit per block of 2^mshift cubed cells, set when any cell of the block is occupied or
-                              // has an index >= cells.len(); at most kMacroWords words, staged in shared memory by k_traverse
-    unsigned mshift, mrx, mry, mwords;
     const unsigned* refs;
     const double* tri;
-    const double* sph;        // 32 B per triangle: centre of the vertices' bounding box + inflated squared radius + guard (see cull_sphere)
+    const float4* sphr;       // 16 B per REFERENCE (same order as refs): bounding sphere of the referenced triangle (see cull_sphere)
     const double* shd;
 };
 
@@ -339,13 +336,14 @@ __device__ __forceinline__ bool hit_triangle(const TriPos& p, D3 o, D3 d, double
 
 // Conservative pre-test of Triangle::intersects: true = the (infinite) line of the ray stays outside the triangle's bounding
 // sphere by so much that the reference's f64 Moller-Trumbore arithmetic is certain to return None, so the candidate can be
-// dropped without evaluating it.  The sphere record holds the centre c, r2 = (r (1 + 1e-6) + 1e-9 (1 + |c|))^2 and
-// lim = 1e17 r2.  |cross(c - o, d)|^2 > r2 |d|^2  <=>  distance(line, c) > inflated radius.  Rounding of the cross product
-// is <= ~9e-16 |c - o| |d|, covered by the 1e-6 relative inflation whenever |c - o|^2 < lim (else: not culled); the
-// reference's own rounding can move its barycentrics by <= ~1e-9 of an edge, orders of magnitude inside the inflation.
-// NaN anywhere compares false: not culled.
-__device__ __forceinline__ bool cull_sphere(double cx, double cy, double cz, double r2, D3 o, D3 d, double dd) {
-    const D3 oc = d3(cx - o.x, cy - o.y, cz - o.z);
+// dropped without evaluating it.  The record holds an f32 centre c and an f32 radius R >= r (1 + 1e-6) + 1e-9 (1 + |c|) +
+// |c - c_exact| (rounded up), r = distance from the exact centre to the farthest vertex.  All arithmetic here is f64:
+// |cross(c - o, d)|^2 > R^2 |d|^2  <=>  distance(line, c) > R.  Rounding of the cross product is <= ~9e-16 |c - o| |d|,
+// covered by the 1e-6 relative inflation whenever |c - o|^2 < 1e17 R^2 (else: not culled); the reference's own rounding can
+// move its barycentrics by <= ~1e-9 of an edge, orders of magnitude inside the inflation.  NaN compares false: not culled.
+__device__ __forceinline__ bool cull_sphere(float4 sp, D3 o, D3 d, double dd) {
+    const double r2 = (double)sp.w * (double)sp.w;
+    const D3 oc = d3((double)sp.x - o.x, (double)sp.y - o.y, (double)sp.z - o.z);
     const D3 cr = cross(oc, d);
     return dot(cr, cr) > r2 * dd && dot(oc, oc) * 1e-17 < r2;
 }
@@ -675,7 +673,7 @@ struct TravWarpShared {
     unsigned prefix[33];               // exclusive prefix of the pooled list lengths
     unsigned kstart[32];               // first reference of the lane's cell
     double dd[32];                     // |d|^2 of the lane's ray
-    unsigned s_pos[64], s_ti[64];      // ring of candidates that survived the sphere pre-test: list position, triangle
+    unsigned s_pos[64];                // ring of candidates that survived the sphere pre-test: list position
     unsigned char s_owner[64];         // ... and the lane that owns the ray
 };
 
@@ -692,10 +690,7 @@ __device__ unsigned long long g_trav_prof[8];
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(const __grid_constant__ DevGrid g, const __grid_constant__ TraverseArgs a) {
     __shared__ TravWarpShared shared[kTravWarps];
-    __shared__ unsigned macro[kMacroWords];
     TravWarpShared& sh = shared[threadIdx.x >> 5];
-    for (unsigned w = threadIdx.x; w < g.mwords; w += blockDim.x) macro[w] = __ldg(&g.mocc[w]);
-    __syncthreads();
     const unsigned n = *a.n_ptr;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt = (1u << lane) - 1u;
@@ -708,9 +703,7 @@ __global__ void __launch_bounds__(kBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(cons
     // DDA state of MY ray (acc_grid.rs:100-125)
     double tmx = 0, tmy = 0, tmz = 0, tdx = 0, tdy = 0, tdz = 0;
     int cx = 0, cy = 0, cz = 0, sx = 1, sy = 1, sz = 1;
-    bool inside = false;                    // current_cell lies inside the grid on every axis (stays true once true)
     const unsigned rx = (unsigned)g.res[0], ry = (unsigned)g.res[1], rz = (unsigned)g.res[2];
-    const unsigned ms = g.mshift, mrx = g.mrx, mry = g.mry;
     unsigned ray = 0, k = 0, cnt = 0;
     unsigned n_cells = 0, n_tests = 0;
 #if defined(RM_TRAV_PROFILE)
@@ -740,7 +733,6 @@ __global__ void __launch_bounds__(kBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(cons
                     const unsigned neg = (unsigned)__double2hiint(q1);
                     sx = (neg & 1u) ? -1 : 1; sy = (neg & 2u) ? -1 : 1; sz = (neg & 4u) ? -1 : 1;
                     ray = (unsigned)__double2loint(q2);
-                    inside = (unsigned)cx < rx && (unsigned)cy < ry && (unsigned)cz < rz;
                     sh.ray[lane][0] = make_double2(ox, oy);
                     sh.ray[lane][1] = make_double2(oz, dx);
                     sh.ray[lane][2] = make_double2(dy, dz);
@@ -830,39 +822,37 @@ __global__ void __launch_bounds__(kBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(cons
         unsigned best_pos = ~0u;
         __syncwarp();
         // item -> (owner lane, list position, triangle): owner = last lane whose exclusive prefix is <= item
-        auto locate = [&](unsigned item, unsigned& owner, unsigned& pos, unsigned& ti) {
+        auto locate = [&](unsigned item, unsigned& owner, unsigned& pos) {
             unsigned lo = 0;
 #pragma unroll
             for (unsigned w = 16; w; w >>= 1)
                 if (sh.prefix[lo + w] <= item) lo += w;
             owner = lo;
             pos = sh.kstart[lo] + (item - sh.prefix[lo]);
-            ti = __ldg(&g.refs[pos]);
         };
-        // Two stages, both with full lanes.  Stage 1: a round of 32 candidates is located, their bounding-sphere records
-        // (32 B) fetched, and the candidates whose ray provably misses are dropped; survivors are appended (ballot
-        // compaction, order kept) to a ring in shared memory.  Stage 2, whenever 32 survivors wait (or the pool is
-        // exhausted): the real Triangle::intersects on the 96-B records.
-        unsigned owner = 0, pos = 0, ti = 0;
-        if (lane < total) locate(lane, owner, pos, ti);
+        // Two stages, both with full lanes.  Stage 1: a round of 32 candidates is located, their bounding spheres (16 B,
+        // contiguous per cell: a coalesced read, fetched one round ahead) tested, and the candidates whose ray provably
+        // misses are dropped; survivors are appended (ballot compaction, order kept) to a ring in shared memory.
+        // Stage 2, whenever 32 survivors wait (or the pool is exhausted): reference -> 96-B record -> Triangle::intersects.
+        unsigned owner = 0, pos = 0;
+        float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < total) { locate(lane, owner, pos); sp = __ldg(&g.sphr[pos]); }
         unsigned base = 0, q_head = 0, q_count = 0;          // warp-uniform
         for (;;) {
             if (base < total && q_count < 32u) {
                 const bool valid = base + lane < total;
-                const unsigned c_owner = owner, c_pos = pos, c_ti = ti;
-                double scx = 0, scy = 0, scz = 0, sr2 = 0;
-                if (valid) ld256_nc(g.sph + (size_t)c_ti * 4, scx, scy, scz, sr2);
-                // the next round's reference is fetched while this round's sphere is in flight
-                if (base + 32u + lane < total) locate(base + 32u + lane, owner, pos, ti);
+                const unsigned c_owner = owner, c_pos = pos;
+                const float4 c_sp = sp;
+                if (base + 32u + lane < total) { locate(base + 32u + lane, owner, pos); sp = __ldg(&g.sphr[pos]); }
                 bool pass = false;
                 if (valid) {
                     const double2 r0 = sh.ray[c_owner][0], r1 = sh.ray[c_owner][1], r2 = sh.ray[c_owner][2];
-                    pass = !cull_sphere(scx, scy, scz, sr2, d3(r0.x, r0.y, r1.x), d3(r1.y, r2.x, r2.y), sh.dd[c_owner]);
+                    pass = !cull_sphere(c_sp, d3(r0.x, r0.y, r1.x), d3(r1.y, r2.x, r2.y), sh.dd[c_owner]);
                 }
                 const unsigned m = __ballot_sync(FULL, pass);
                 if (pass) {
                     const unsigned slot = (q_head + q_count + __popc(m & lt)) & 63u;
-                    sh.s_pos[slot] = c_pos; sh.s_ti[slot] = c_ti; sh.s_owner[slot] = (unsigned char)c_owner;
+                    sh.s_pos[slot] = c_pos; sh.s_owner[slot] = (unsigned char)c_owner;
                 }
                 q_count += __popc(m);
                 base += 32u;
@@ -878,7 +868,7 @@ __global__ void __launch_bounds__(kBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(cons
             if (valid) {
                 const unsigned slot = (q_head + lane) & 63u;
                 c_owner = sh.s_owner[slot]; c_pos = sh.s_pos[slot];
-                const TriPos tp = load_triangle(g.tri + (size_t)sh.s_ti[slot] * 12);
+                const TriPos tp = load_triangle(g.tri + (size_t)__ldg(&g.refs[c_pos]) * 12);
                 const double2 r0 = sh.ray[c_owner][0], r1 = sh.ray[c_owner][1], r2 = sh.ray[c_owner][2];
                 double t;
                 if (hit_triangle(tp, d3(r0.x, r0.y, r1.x), d3(r1.y, r2.x, r2.y), t)) {
