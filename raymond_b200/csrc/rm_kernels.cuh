@@ -339,13 +339,15 @@ __device__ __forceinline__ bool hit_triangle(const TriPos& p, D3 o, D3 d, double
 // dropped without evaluating it.  The record holds an f32 centre c and an f32 radius R >= r (1 + 1e-6) + 1e-9 (1 + |c|) +
 // |c - c_exact| (rounded up), r = distance from the exact centre to the farthest vertex.  All arithmetic here is f64:
 // |cross(c - o, d)|^2 > R^2 |d|^2  <=>  distance(line, c) > R.  Rounding of the cross product is <= ~9e-16 |c - o| |d|,
-// covered by the 1e-6 relative inflation whenever |c - o|^2 < 1e17 R^2 (else: not culled); the reference's own rounding can
-// move its barycentrics by <= ~1e-9 of an edge, orders of magnitude inside the inflation.  NaN compares false: not culled.
-__device__ __forceinline__ bool cull_sphere(float4 sp, D3 o, D3 d, double dd) {
+// covered by the 1e-6 relative inflation whenever |c - o|^2 < 1e17 R^2; `lim` = 1.01e-17 * (largest squared distance
+// from the ray origin to the grid's box, which holds every centre) is that guard, evaluated once per ray (else: not
+// culled).  The reference's own rounding can move its barycentrics by <= ~1e-9 of an edge, orders of magnitude inside
+// the inflation.  NaN compares false: not culled.
+__device__ __forceinline__ bool cull_sphere(float4 sp, D3 o, D3 d, double dd, double lim) {
     const double r2 = (double)sp.w * (double)sp.w;
     const D3 oc = d3((double)sp.x - o.x, (double)sp.y - o.y, (double)sp.z - o.z);
     const D3 cr = cross(oc, d);
-    return dot(cr, cr) > r2 * dd && dot(oc, oc) * 1e-17 < r2;
+    return dot(cr, cr) > r2 * dd && lim < r2;
 }
 
 // Scene::intersect keeps the first object among equal distances (strict <, scene.rs:61).  Objects are
@@ -670,9 +672,9 @@ struct TravWarpShared {
     double2 ray[32][3];                // {o.x o.y} {o.z d.x} {d.y d.z} of the lane's ray (three 128-bit accesses)
     unsigned long long cand_t[32];     // this round's smallest distance bits per ray
     unsigned cand_pos[32];             // ... and the earliest list position that has it
-    unsigned prefix[33];               // exclusive prefix of the pooled list lengths
-    unsigned kstart[32];               // first reference of the lane's cell
-    double dd[32];                     // |d|^2 of the lane's ray
+    unsigned olane[32];                // q-th lane that contributes a list to the pool
+    unsigned odelta[32];               // ... and (first reference of its cell) - (its first item): position = item + odelta
+    double2 dd_lim[32];                // |d|^2 of the lane's ray, and the guard of cull_sphere
     unsigned s_pos[64];                // ring of candidates that survived the sphere pre-test: list position
     unsigned char s_owner[64];         // ... and the lane that owns the ray
 };
@@ -736,7 +738,11 @@ __global__ void __launch_bounds__(kBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(cons
                     sh.ray[lane][0] = make_double2(ox, oy);
                     sh.ray[lane][1] = make_double2(oz, dx);
                     sh.ray[lane][2] = make_double2(dy, dz);
-                    sh.dd[lane] = (dx * dx + dy * dy) + dz * dz;
+                    {
+                        const double mx = fmax(fabs(g.bmin[0] - ox), fabs(g.bmax[0] - ox)), my = fmax(fabs(g.bmin[1] - oy), fabs(g.bmax[1] - oy)),
+                                     mz = fmax(fabs(g.bmin[2] - oz), fabs(g.bmax[2] - oz));
+                        sh.dd_lim[lane] = make_double2((dx * dx + dy * dy) + dz * dz, ((mx * mx + my * my) + mz * mz) * 1.01e-17);
+                    }
                     state = TS_LOOK;
                 }
             }
@@ -813,22 +819,34 @@ __global__ void __launch_bounds__(kBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(cons
         }
         const unsigned total = __shfl_sync(FULL, incl, 31);
         if (total == 0) continue;
-        if (lane == 0) sh.prefix[0] = 0u;
-        sh.prefix[lane + 1] = incl;
-        sh.kstart[lane] = k;
+        // The pool: items [excl, excl + mine) belong to this lane's cell.  Contributing lanes are compacted into
+        // olane / odelta; a round of 32 consecutive items finds its owners with one ballot and one redux:
+        //   first = contributors whose list starts at or before the round, bits = list starts inside the round
+        const unsigned excl = incl - mine;
+        {
+            const unsigned contrib = __ballot_sync(FULL, mine != 0u);
+            if (mine) {
+                const unsigned q = __popc(contrib & lt);
+                sh.olane[q] = lane;
+                sh.odelta[q] = k - excl;
+            }
+        }
         sh.cand_t[lane] = ~0ull;
         sh.cand_pos[lane] = ~0u;
         unsigned long long best_t = kClosest0;       // per-cell closest of MY ray
         unsigned best_pos = ~0u;
         __syncwarp();
-        // item -> (owner lane, list position, triangle): owner = last lane whose exclusive prefix is <= item
-        auto locate = [&](unsigned item, unsigned& owner, unsigned& pos) {
-            unsigned lo = 0;
-#pragma unroll
-            for (unsigned w = 16; w; w >>= 1)
-                if (sh.prefix[lo + w] <= item) lo += w;
-            owner = lo;
-            pos = sh.kstart[lo] + (item - sh.prefix[lo]);
+        // (owner lane, list position) of item rbase + lane; rbase is warp-uniform and every lane takes part
+        auto locate = [&](unsigned rbase, unsigned& owner, unsigned& pos) {
+            const unsigned first = __popc(__ballot_sync(FULL, mine != 0u && excl <= rbase)) - 1u;
+            const unsigned off = excl - rbase;                                   // 1..31 when my list starts inside the round
+            const unsigned bits = __reduce_or_sync(FULL, (mine != 0u && off - 1u < 31u) ? (1u << off) : 0u);
+            const unsigned item = rbase + lane;
+            if (item < total) {
+                const unsigned q = first + __popc(bits & ((2u << lane) - 1u));
+                owner = sh.olane[q];
+                pos = item + sh.odelta[q];
+            }
         };
         // Two stages, both with full lanes.  Stage 1: a round of 32 candidates is located, their bounding spheres (16 B,
         // contiguous per cell: a coalesced read, fetched one round ahead) tested, and the candidates whose ray provably
@@ -836,18 +854,23 @@ __global__ void __launch_bounds__(kBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(cons
         // Stage 2, whenever 32 survivors wait (or the pool is exhausted): reference -> 96-B record -> Triangle::intersects.
         unsigned owner = 0, pos = 0;
         float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lane < total) { locate(lane, owner, pos); sp = __ldg(&g.sphr[pos]); }
+        locate(0u, owner, pos);
+        if (lane < total) sp = __ldg(&g.sphr[pos]);
         unsigned base = 0, q_head = 0, q_count = 0;          // warp-uniform
         for (;;) {
             if (base < total && q_count < 32u) {
                 const bool valid = base + lane < total;
                 const unsigned c_owner = owner, c_pos = pos;
                 const float4 c_sp = sp;
-                if (base + 32u + lane < total) { locate(base + 32u + lane, owner, pos); sp = __ldg(&g.sphr[pos]); }
+                if (base + 32u < total) {                    // warp-uniform
+                    locate(base + 32u, owner, pos);
+                    if (base + 32u + lane < total) sp = __ldg(&g.sphr[pos]);
+                }
                 bool pass = false;
                 if (valid) {
                     const double2 r0 = sh.ray[c_owner][0], r1 = sh.ray[c_owner][1], r2 = sh.ray[c_owner][2];
-                    pass = !cull_sphere(c_sp, d3(r0.x, r0.y, r1.x), d3(r1.y, r2.x, r2.y), sh.dd[c_owner]);
+                    const double2 dl = sh.dd_lim[c_owner];
+                    pass = !cull_sphere(c_sp, d3(r0.x, r0.y, r1.x), d3(r1.y, r2.x, r2.y), dl.x, dl.y);
                 }
                 const unsigned m = __ballot_sync(FULL, pass);
                 if (pass) {
