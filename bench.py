@@ -33,9 +33,9 @@ METRIC = "Msamples/sec (paths x 5 bounces), GoldDragon 1920x1080 500 spp"
 UNIT = "Msamples/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, from the ncu --set full capture in profiles/ (None = not captured)
 NCU_TRAFFIC_PER_UNIT = {
-    # profiles/r1_v7_traverse_ncu_summary.md: the k_traverse launches of depth 1, 2, 3 of one 8-spp batch (10.4 M grid rays)
-    # read + wrote 1.146 + 2.318 + 1.337 GB of DRAM = 460 B per grid ray
-    "k_traverse": 460.0,
+    # profiles/r1_v10_traverse_ncu_summary.md: the k_traverse launches of depth 1, 2, 3 of one 16-spp batch (20.9 M grid rays)
+    # read + wrote 2.11 + 3.48 + 1.94 GB of DRAM = 360 B per grid ray
+    "k_traverse": 360.0,
 }
 
 
@@ -289,6 +289,7 @@ def bench_ours(args):
         counted.close()
         total_ms = sum(sum(v) for v in d_ms.values())
         stages, per_kernel = [], {}
+        kernel_bytes, survive = {}, {}
         for d in range(0, A.STAGE_SLOTS):
             for k in kinds:
                 if d_launch[k][d] == 0:
@@ -306,6 +307,10 @@ def bench_ours(args):
                     g_ = max(cs["grid_rays"][d], 1)
                     C_, T_ = cs["cells"][d] / g_, cs["triangle_tests"][d] / g_
                     units, per_unit = d_grid[d], 64.0 + 8.0 * C_ + 76.0 * T_
+                    # what THIS kernel has to move for the same decisions: 128-B record + 16-B hit, a 4-B occupancy word per cell, an 8-B record
+                    # per occupied cell, a 16-B bounding sphere per candidate, reference + positions (100 B) per candidate not proven a miss
+                    kernel_bytes[d] = (144.0 + 4.0 * C_ + 8.0 * cs["occupied_cells"][d] / g_ + 16.0 * T_ + 100.0 * cs["evaluated_tests"][d] / g_) * d_grid[d]
+                    survive[d] = cs["evaluated_tests"][d] / max(cs["triangle_tests"][d], 1)
                 else:
                     # shade: ray + throughput + id + hit in (92 B), next ray out (76 B) or radiance out (24 B); +144 B (positions, normals) per shaded triangle
                     units = d_rays[d]
@@ -334,10 +339,19 @@ def bench_ours(args):
                     "unit_name": "grid ray" if top == "traverse" else ("path" if top == "accumulate" else "ray"),
                     "launch_ms_avg": pk["ms"] / max(pk["launches"], 1), "launches": pk["launches"], "share_of_step": pk["ms"] / max(total_ms, 1e-9),
                     "per_kernel_share": {"k_" + k: v["ms"] / max(total_ms, 1e-9) for k, v in per_kernel.items()},
-                    "traffic_note": "ncu dram bytes per grid ray (460 B, depths 1-3 of an 8-spp batch) x grid rays per launch; far BELOW the algorithmic bytes because the "
+                    "kernel_model": ({"bytes_per_unit": sum(kernel_bytes.values()) / max(pk["units"], 1),
+                                      "achieved_gbs": sum(kernel_bytes.values()) / (pk["ms"] * 1e-3) / 1e9,
+                                      "frac_of_hbm_peak": sum(kernel_bytes.values()) / (pk["ms"] * 1e-3) / 1e9 / peak,
+                                      "tests_evaluated_fraction": sum(survive.values()) / max(len(survive), 1),
+                                      "what": "bytes this kernel's own algorithm moves per grid ray: 144 + 4 C + 8 C_occupied + 16 T + 100 T_evaluated "
+                                              "(the bounding-sphere pre-test proves most of the reference's T triangle tests to be misses without fetching them)"}
+                                     if top == "traverse" else None),
+                    "traffic_note": "ncu dram bytes per grid ray (360 B, depths 1-3 of a 16-spp batch) x grid rays per launch; far BELOW the algorithmic bytes because the "
                                     "150 MB traversal set is L2-resident and every triangle is fetched by many rays (L2 hit 85-89 %)",
-                    "note": "f64 no-FMA traversal of an L2-resident grid: the binding limits are instruction issue (ncu: 50-55 % issue-active, "
-                            "FP64 pipe 19-21 %, LSU data pipe 59 %) and L2 latency, not HBM (3-7 % of peak); see DESIGN.md section 6 and profiles/"}
+                    "note": "achieved/frac use the REFERENCE algorithm's bytes (SURVEY 8d: 64 + 8 C + 76 T); the kernel makes the same decisions while "
+                            "fetching far less (kernel_model), so frac can exceed 1. f64 no-FMA traversal of an L2-resident grid: the binding limits "
+                            "are instruction issue (ncu: 60-68 % issue-active, FP64 pipe 22 %, LSU data pipe 43-50 %) and L2 latency, not HBM "
+                            "(4-7 % of peak); see DESIGN.md section 6 and profiles/"}
     dr.close()
     del dr
 

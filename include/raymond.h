@@ -332,6 +332,8 @@ typedef struct rm_stage_stats {
     uint64_t cells[RM_STAGE_SLOTS];
     uint64_t triangle_tests[RM_STAGE_SLOTS];
     uint64_t shaded_triangles[RM_STAGE_SLOTS];
+    uint64_t evaluated_tests[RM_STAGE_SLOTS];  /* of triangle_tests, the ones NOT proven misses by the bounding-sphere pre-test (RM_FLAG_COUNT_WORK) */
+    uint64_t occupied_cells[RM_STAGE_SLOTS];   /* of cells, the ones with a non-empty list (RM_FLAG_COUNT_WORK) */
 } rm_stage_stats;
 int rm_renderer_stage_stats(rm_renderer* r, rm_stage_stats* out);
 void rm_renderer_destroy(rm_renderer* r);

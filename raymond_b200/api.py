@@ -107,12 +107,12 @@ KERNEL_KINDS = ("setup", "traverse", "shade", "accumulate")
 
 class StageStatsC(C.Structure):
     _fields_ = [("ms", (C.c_double * STAGE_SLOTS) * 4), ("launches", (C.c_uint64 * STAGE_SLOTS) * 4)] + \
-               [(n, C.c_uint64 * STAGE_SLOTS) for n in ("rays", "grid_rays", "cells", "triangle_tests", "shaded_triangles")]
+               [(n, C.c_uint64 * STAGE_SLOTS) for n in ("rays", "grid_rays", "cells", "triangle_tests", "shaded_triangles", "evaluated_tests", "occupied_cells")]
 
     def as_dict(self) -> dict:
         d = {"ms": {k: list(self.ms[i]) for i, k in enumerate(KERNEL_KINDS)},
              "launches": {k: list(self.launches[i]) for i, k in enumerate(KERNEL_KINDS)}}
-        for n in ("rays", "grid_rays", "cells", "triangle_tests", "shaded_triangles"):
+        for n in ("rays", "grid_rays", "cells", "triangle_tests", "shaded_triangles", "evaluated_tests", "occupied_cells"):
             d[n] = list(getattr(self, n))
         return d
 

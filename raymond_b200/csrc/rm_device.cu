@@ -826,6 +826,8 @@ int rm_renderer_stage_stats(rm_renderer* r, rm_stage_stats* out) {
         out->cells[i] = t.cells[i];
         out->triangle_tests[i] = t.tests[i];
         out->shaded_triangles[i] = t.shaded[i];
+        out->evaluated_tests[i] = t.survivors[i];
+        out->occupied_cells[i] = t.occupied[i];
     }
     return RM_OK;
 }

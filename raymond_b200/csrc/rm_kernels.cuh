@@ -107,7 +107,7 @@ constexpr int kTravDoubles = 16;
 
 struct DevTotals {
     unsigned long long samples, rays, nonfinite;
-    unsigned long long stage_rays[RM_STAGE_SLOTS], grid_rays[RM_STAGE_SLOTS], cells[RM_STAGE_SLOTS], tests[RM_STAGE_SLOTS], shaded[RM_STAGE_SLOTS];
+    unsigned long long stage_rays[RM_STAGE_SLOTS], grid_rays[RM_STAGE_SLOTS], cells[RM_STAGE_SLOTS], tests[RM_STAGE_SLOTS], shaded[RM_STAGE_SLOTS], survivors[RM_STAGE_SLOTS], occupied[RM_STAGE_SLOTS];
 };
 
 // Per-batch device counters, all indexed by depth (zeroed once per batch).
@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(kBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(cons
     int cx = 0, cy = 0, cz = 0, sx = 1, sy = 1, sz = 1;
     const unsigned rx = (unsigned)g.res[0], ry = (unsigned)g.res[1], rz = (unsigned)g.res[2];
     unsigned ray = 0, k = 0, cnt = 0;
-    unsigned n_cells = 0, n_tests = 0;
+    unsigned n_cells = 0, n_tests = 0, n_surv = 0, n_occ = 0;
 #if defined(RM_TRAV_PROFILE)
     unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long prof_t = clock64();
@@ -806,7 +806,7 @@ __global__ void __launch_bounds__(kBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(cons
         if (state == TS_READY) {
             const uint2 cell = __ldg(&g.cells[k]);
             k = cell.x; cnt = cell.y;
-            if (COUNT) n_tests += cnt;
+            if (COUNT) { n_tests += cnt; n_occ++; }
         }
         RM_PROF_MARK(1);
         // ---- B: pooled triangle tests of every ready cell
@@ -878,6 +878,7 @@ __global__ void __launch_bounds__(kBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(cons
                     sh.s_pos[slot] = c_pos; sh.s_owner[slot] = (unsigned char)c_owner;
                 }
                 q_count += __popc(m);
+                if (COUNT && pass) n_surv++;
                 base += 32u;
                 __syncwarp();
                 continue;
@@ -939,9 +940,12 @@ __global__ void __launch_bounds__(kBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(cons
 #endif
     if (COUNT) {
         const unsigned c = __reduce_add_sync(FULL, n_cells), t = __reduce_add_sync(FULL, n_tests);
+        const unsigned sv = __reduce_add_sync(FULL, n_surv), oc = __reduce_add_sync(FULL, n_occ);
         if (lane == 0) {
             atomicAdd(&a.totals->cells[stage_slot(a.depth)], (unsigned long long)c);
             atomicAdd(&a.totals->tests[stage_slot(a.depth)], (unsigned long long)t);
+            atomicAdd(&a.totals->survivors[stage_slot(a.depth)], (unsigned long long)sv);
+            atomicAdd(&a.totals->occupied[stage_slot(a.depth)], (unsigned long long)oc);
         }
     }
 }
