@@ -39,6 +39,9 @@ NCU_TRAFFIC_PER_UNIT = {
 }
 
 
+print_line = None
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -199,7 +202,7 @@ def bench_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print_line(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------- GPU arm
@@ -414,13 +417,21 @@ def bench_ours(args):
             "stages": stages, "host_grid_build_s": host_build_s, "mean_radiance": mean_radiance,
             "nonfinite_samples": int(s1["nonfinite_samples"]),
         }
-        print(json.dumps(line), flush=True)
+        print_line(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
     args = parse_args()
+    # stdout carries exactly ONE JSON line: anything libraries write to file descriptor 1 meanwhile (NCCL prints its version
+    # banner there) is sent to stderr, and the descriptor is restored for the final print
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(saved, "w")
+    global print_line
+    print_line = lambda text: (real_stdout.write(text + "\n"), real_stdout.flush())
     if args.impl == "reference":
         bench_reference(args)
     else:
