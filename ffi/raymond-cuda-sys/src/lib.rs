@@ -27,6 +27,7 @@ pub enum rm_mesh {} pub enum rm_grid {} pub enum rm_scene {} pub enum rm_task {}
 
 extern "C" {
     pub fn rm_last_error() -> *const c_char;
+    pub fn rm_last_status() -> c_int;
     pub fn rm_mesh_from_triangles(t: *const rm_triangle, n: usize) -> *mut rm_mesh;      // Mesh::new          mesh.rs:16
     pub fn rm_mesh_load_ply(path: *const c_char) -> *mut rm_mesh;                        // Mesh::load_ply     mesh.rs:58
     pub fn rm_mesh_translate(m: *mut rm_mesh, t: rm_vec3) -> c_int;                      // bake_transform     mesh.rs:48

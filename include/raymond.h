@@ -53,6 +53,8 @@ typedef enum rm_status {
 } rm_status;
 
 const char* rm_last_error(void);
+/* rm_status of the last failure on the calling thread — for the entry points that return a handle (NULL on failure). */
+int rm_last_status(void);
 int rm_abi_version(void);
 
 /* ------------------------------------------------------------- plain types */

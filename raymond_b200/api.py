@@ -121,7 +121,7 @@ TILE_CALLBACK = C.CFUNCTYPE(None, C.POINTER(TileC), C.c_void_p)
 
 # every symbol include/raymond.h declares (tests check the library exports them all)
 ABI_SYMBOLS = [
-    "rm_last_error", "rm_abi_version",
+    "rm_last_error", "rm_last_status", "rm_abi_version",
     "rm_mesh_from_triangles", "rm_mesh_load_ply", "rm_mesh_translate", "rm_mesh_triangle_count", "rm_mesh_bounds", "rm_mesh_triangles",
     "rm_mesh_destroy", "rm_grid_build", "rm_grid_build_on_device", "rm_grid_retain", "rm_grid_release", "rm_grid_get_info", "rm_grid_get_cells",
     "rm_scene_create", "rm_scene_add_sphere", "rm_scene_add_plane", "rm_scene_add_grid", "rm_scene_object_count", "rm_scene_destroy",
@@ -148,6 +148,7 @@ def lib():
     P = C.POINTER
     sig = {
         "rm_last_error": (C.c_char_p, []),
+        "rm_last_status": (i32, []),
         "rm_abi_version": (i32, []),
         "rm_mesh_from_triangles": (vp, [vp, sz]),
         "rm_mesh_load_ply": (vp, [C.c_char_p]),
@@ -219,7 +220,8 @@ def _check(status: int) -> None:
 
 def _require(handle, what: str, status: int = RM_ERR_CUDA):
     if not handle:
-        raise RaymondError(status, f"{what}: {last_error()}")
+        st = lib().rm_last_status()
+        raise RaymondError(st if st < 0 else status, f"{what}: {last_error()}")
     return handle
 
 

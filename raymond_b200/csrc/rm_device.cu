@@ -613,12 +613,12 @@ static void harvest_events(rm_renderer* r) {
 extern "C" {
 
 rm_device_scene* rm_device_scene_create(const rm_scene* scene, int device) {
-    if (!scene) { set_error("rm_device_scene_create: null scene"); return nullptr; }
+    if (!scene) { fail(RM_ERR_INVALID_ARGUMENT, "rm_device_scene_create: null scene"); return nullptr; }
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || device < 0 || device >= count) {
-        set_error(std::string("no usable CUDA device ") + std::to_string(device) + " (" + (e != cudaSuccess ? cudaGetErrorString(e) : "ordinal out of range") +
-                  "); this library has no CPU path");
+        fail(RM_ERR_CUDA, std::string("no usable CUDA device ") + std::to_string(device) + " (" + (e != cudaSuccess ? cudaGetErrorString(e) : "ordinal out of range") +
+                              "); this library has no CPU path");
         return nullptr;
     }
     rm_device_scene* ds = new rm_device_scene();
@@ -672,7 +672,7 @@ int rm_primary_rays_device(const rm_camera_settings* camera, int device, rm_ray*
 int rm_scene_intersect(const rm_scene* scene, int device, const rm_ray* rays, size_t count, int64_t* obj, uint64_t* sub, double* distance) {
     if (!scene || (!rays && count)) return fail(RM_ERR_INVALID_ARGUMENT, "rm_scene_intersect: null argument");
     rm_device_scene* ds = rm_device_scene_create(scene, device);
-    if (!ds) return RM_ERR_CUDA;
+    if (!ds) return rm_last_status();
     int st = RM_OK;
     rm_ray* d_rays = nullptr; int64_t* d_obj = nullptr; uint64_t* d_sub = nullptr; double* d_t = nullptr;
     auto cleanup = [&]() { dev_free(d_rays); dev_free(d_obj); dev_free(d_sub); dev_free(d_t); delete ds; };
@@ -698,7 +698,7 @@ int rm_scene_intersect(const rm_scene* scene, int device, const rm_ray* rays, si
 }
 
 rm_renderer* rm_renderer_create_on(rm_device_scene* ds, const rm_settings* settings, const rm_gpu_options* options) {
-    if (!ds || !settings) { set_error("rm_renderer_create_on: null argument"); return nullptr; }
+    if (!ds || !settings) { fail(RM_ERR_INVALID_ARGUMENT, "rm_renderer_create_on: null argument"); return nullptr; }
     rm_renderer* r = new rm_renderer();
     r->ds = ds;
     r->settings = *settings;
@@ -710,7 +710,7 @@ rm_renderer* rm_renderer_create_on(rm_device_scene* ds, const rm_settings* setti
 }
 
 rm_renderer* rm_renderer_create(const rm_scene* scene, const rm_settings* settings, const rm_gpu_options* options) {
-    if (!scene || !settings) { set_error("rm_renderer_create: null argument"); return nullptr; }
+    if (!scene || !settings) { fail(RM_ERR_INVALID_ARGUMENT, "rm_renderer_create: null argument"); return nullptr; }
     rm_device_scene* ds = rm_device_scene_create(scene, options ? options->device : 0);
     if (!ds) return nullptr;
     rm_renderer* r = rm_renderer_create_on(ds, settings, options);

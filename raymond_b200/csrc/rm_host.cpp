@@ -16,9 +16,10 @@
 namespace rm {
 
 static thread_local std::string g_last_error;
+static thread_local int g_last_status = RM_OK;
 
-void set_error(const std::string& msg) { g_last_error = msg; }
-int fail(int status, const std::string& msg) { g_last_error = msg; return status; }
+void set_error(const std::string& msg) { g_last_error = msg; if (g_last_status == RM_OK) g_last_status = RM_ERR_INVALID_ARGUMENT; }
+int fail(int status, const std::string& msg) { g_last_error = msg; g_last_status = status; return status; }
 
 // ------------------------------------------------------------------ bounds
 
@@ -295,6 +296,7 @@ using namespace rm;
 extern "C" {
 
 const char* rm_last_error(void) { return g_last_error.c_str(); }
+int rm_last_status(void) { return g_last_status; }
 int rm_abi_version(void) { return RM_ABI_VERSION; }
 
 rm_mesh* rm_mesh_from_triangles(const rm_triangle* triangles, size_t count) {

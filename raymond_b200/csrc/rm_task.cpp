@@ -102,7 +102,7 @@ void drive(rm_task* t) {
 extern "C" {
 
 rm_task* rm_render_tiled(const rm_scene* scene, const rm_settings* settings, const rm_gpu_options* options) {
-    if (!scene || !settings) { set_error("rm_render_tiled: null argument"); return nullptr; }
+    if (!scene || !settings) { fail(RM_ERR_INVALID_ARGUMENT, "rm_render_tiled: null argument"); return nullptr; }
     rm_task* t = new rm_task();
     t->settings = *settings;
     if (options) t->options = *options;

@@ -1,0 +1,93 @@
+"""GPU edge cases of the path: several grids in one scene (one traversal pass per grid object), a grid shared by two objects
+(Arc<AccGrid>), empty scenes, tiny and ragged frames, deep bounce limits, tiles larger than the frame."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from raymond_b200 import api as A
+from raymond_b200 import fixtures as F
+
+from test_gpu_render import compare_same_stream, gpu_render
+from util import assert_hits_equal, oracle_scene, product_scene, settings
+
+pytestmark = pytest.mark.gpu
+
+
+def two_mesh_scene():
+    a = F.translate(F.bumpy_sphere(30, 60, 0.6, 0.1, (1.0, 0.8, 0.6)), (-0.7, -0.3, 3.0))
+    b = F.translate(F.dragon_standin(120, 30), (0.5, -0.2, 3.4))
+    return [F.RED_SPHERE, ("grid", a, ("Metal", (0.9, 0.9, 0.9), 0.05)), ("grid", b, F.DRAGON_MATERIAL)] + F.BOX_PLANES
+
+
+def test_two_grids_bit_exact_and_render():
+    objs = two_mesh_scene()
+    cam = F.camera(200, 120)
+    rays = np.concatenate([O.primary_rays(cam), F.random_rays(30000, 4, ((-1.9, 1.9), (-0.9, 1.9), (-1.9, 4.9)))])
+    want = oracle_scene(objs).intersect(rays)
+    assert {1, 2} <= set(want[0].tolist())
+    assert_hits_equal(product_scene(objs).intersect(rays), want, "two grids")
+    g, gs = gpu_render(objs, F.camera(128, 72), 4, seed=3)
+    o, oc = O.render(oracle_scene(objs), F.camera(128, 72), 4, seed=3)
+    compare_same_stream(g, o, 4, "two grids render", max_outlier_frac=0.01)
+
+
+def test_shared_grid_two_objects():
+    """The same Arc<AccGrid> pushed twice with different materials: ties go to the first object (scene.rs:61)."""
+    tris = F.translate(F.bumpy_sphere(20, 40, 0.5), (0.0, 0.0, 3.0))
+    grid = A.AccGrid.build_from_mesh(A.Mesh.new(tris))
+    s = A.Scene()
+    s.push_grid(grid, A.Material.Metal((1, 1, 0.1), 0.15))
+    s.push_grid(grid, A.Material.Diffuse((0.2, 0.9, 0.2), 0.5))
+    osc = O.Scene()
+    og = O.AccGrid.build_from_mesh(O.Mesh.from_triangles(tris))
+    osc.add_grid(og, ("Metal", (1, 1, 0.1), 0.15))
+    osc.add_grid(og, ("Diffuse", (0.2, 0.9, 0.2), 0.5))
+    rays = O.primary_rays(F.camera(160, 120))
+    want = osc.intersect(rays)
+    got = s.intersect(rays)
+    assert_hits_equal(got, want, "shared grid")
+    assert set(got[0].tolist()) == {-1, 0}                    # equal distances: the first object wins
+
+
+def test_empty_scene_and_too_many_objects():
+    s = A.Scene()
+    obj, sub, t = s.intersect(O.primary_rays(F.camera(16, 8)))
+    assert (obj == -1).all()
+    r = A.Renderer(s, settings(F.camera(16, 8), 2), A.GpuOptions(seed=1))
+    r.render(0, 2)
+    assert not r.read_sums().any()
+    big = A.Scene()
+    for i in range(65):
+        big.push_sphere((i * 0.1, 0, 5), 0.01, A.Material.Diffuse((1, 1, 1), 0.5))
+    with pytest.raises(A.RaymondError) as e:
+        big.intersect(np.array([[0, 0, 0, 0, 0, 1.0]]))
+    assert e.value.status == A.RM_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("w,h,tile", [(1, 1, (32, 32)), (33, 7, (32, 32)), (50, 40, (64, 64)), (37, 29, (5, 3))])
+def test_ragged_frames_and_tiles(w, h, tile):
+    objs, cam, spp = F.reflective_spheres(), F.camera(w, h), 3
+    st = settings(cam, spp, tile=tile, spi=1)
+    task = A.render_tiled(product_scene(objs), st, A.GpuOptions(seed=2))
+    task.stats()
+    msgs = []
+    while (m := task.poll()) is not None:
+        msgs.append(m)
+    layout = A.tile_layout(st)
+    assert [tuple(r) for r in layout] == [tuple(r) for r in O.tile_layout(cam, tile).tolist()]
+    fin = [m for m in msgs if m.kind == "TileFinished"]
+    assert len(fin) == len(layout) and sum(m.tile.width * m.tile.height for m in fin) == w * h
+    want, _ = O.render(oracle_scene(objs), cam, spp, seed=2, tile_size=tile)
+    got = np.zeros((h, w, 3))
+    for m in fin:
+        t = m.tile
+        got[t.top:t.top + t.height, t.left:t.left + t.width] = t.data
+    assert np.abs(got - want).max() <= 1e-9 * max(np.abs(want).max(), 1.0) or (np.abs(got - want).max(axis=-1) > 1e-9).mean() < 0.02
+
+
+def test_deep_bounce_limit():
+    objs, cam, spp = F.reflective_spheres(), F.camera(48, 32), 2
+    g, gs = gpu_render(objs, cam, spp, seed=5, bounce_limit=24)
+    o, oc = O.render(oracle_scene(objs), cam, spp, seed=5, bounce_limit=24)
+    compare_same_stream(g, o, spp, "bounce_limit 24", max_outlier_frac=0.02)
+    assert gs["rays"] > 0
