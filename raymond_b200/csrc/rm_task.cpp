@@ -10,6 +10,21 @@
 
 using namespace rm;
 
+// One checkpoint of the render: the whole frame of running sums as it was when the messages were posted.  The
+// reference clones a Tile into every message (src/trace.rs:212-218); here the tiles of one checkpoint share one
+// frame snapshot and are sliced out of it when a message is delivered.
+struct FrameSnapshot {
+    std::vector<rm_vec3> sums;      // W * H, row-major
+    size_t W = 0;
+};
+
+struct PendingMessage {
+    uint32_t kind;
+    size_t sample_count;
+    TileRect rect;
+    std::shared_ptr<FrameSnapshot> frame;
+};
+
 struct rm_task {
     rm_settings settings{};
     rm_gpu_options options{};
@@ -17,7 +32,7 @@ struct rm_task {
     std::thread driver;
     std::mutex mu;
     std::condition_variable cv;
-    std::deque<rm_message> messages;
+    std::deque<PendingMessage> messages;
     bool finished = false;          // alive_thread_count == 0   src/trace.rs:74,89
     int status = RM_OK;
     std::string error;
@@ -28,13 +43,15 @@ struct rm_task {
 
 namespace {
 
-bool make_tile(const TileRect& r, size_t sample_count, const rm_vec3* frame_sums, size_t W, rm_tile* out) {
-    out->sample_count = sample_count;
+// Tile { sample_count, width, height, left, top, data }: an independent copy the receiver owns
+bool make_tile(const PendingMessage& m, rm_tile* out) {
+    const TileRect& r = m.rect;
+    out->sample_count = m.sample_count;
     out->width = r.width; out->height = r.height; out->left = r.left; out->top = r.top;
     out->data = (rm_vec3*)malloc(std::max<size_t>(r.width * r.height, 1) * sizeof(rm_vec3));
     if (!out->data) return false;
     for (size_t y = 0; y < r.height; y++)
-        memcpy(out->data + y * r.width, frame_sums + (r.top + y) * W + r.left, r.width * sizeof(rm_vec3));
+        memcpy(out->data + y * r.width, m.frame->sums.data() + (r.top + y) * m.frame->W + r.left, r.width * sizeof(rm_vec3));
     return true;
 }
 
@@ -42,16 +59,16 @@ void post_tiles(rm_task* t, uint32_t kind, size_t sample_count, const rm_vec3* s
     const size_t W = t->settings.camera_settings.backbuffer_width, H = t->settings.camera_settings.backbuffer_height;
     std::vector<TileRect> tiles = tile_layout(W, H, t->settings.tile_size[0], t->settings.tile_size[1]);
     const int world = t->options.world_size > 1 ? t->options.world_size : 1;
-    std::deque<rm_message> batch;
+    auto frame = std::make_shared<FrameSnapshot>();
+    frame->W = W;
+    frame->sums.assign(sums, sums + W * H);
+    std::deque<PendingMessage> batch;
     for (size_t i = 0; i < tiles.size(); i++) {
         if (t->options.partition == RM_PARTITION_TILES && (int)(i % (size_t)world) != t->options.rank) continue;
-        rm_message m{};
-        m.kind = kind;
-        if (!make_tile(tiles[i], sample_count, sums, W, &m.tile)) continue;
-        batch.push_back(m);
+        batch.push_back(PendingMessage{kind, sample_count, tiles[i], frame});
     }
     std::lock_guard<std::mutex> lk(t->mu);
-    for (rm_message& m : batch) t->messages.push_back(m);
+    for (PendingMessage& m : batch) t->messages.push_back(std::move(m));
     t->cv.notify_all();
 }
 
@@ -116,10 +133,16 @@ rm_task* rm_render_tiled(const rm_scene* scene, const rm_settings* settings, con
 
 int rm_task_poll(rm_task* t, rm_message* out) {
     if (!t || !out) return fail(RM_ERR_INVALID_ARGUMENT, "rm_task_poll: null argument");
-    std::lock_guard<std::mutex> lk(t->mu);
-    if (t->messages.empty()) return 0;
-    *out = t->messages.front();
-    t->messages.pop_front();
+    PendingMessage m;
+    {
+        std::lock_guard<std::mutex> lk(t->mu);
+        if (t->messages.empty()) return 0;
+        m = std::move(t->messages.front());
+        t->messages.pop_front();
+    }
+    out->kind = m.kind;
+    out->reserved = 0;
+    if (!make_tile(m, &out->tile)) return fail(RM_ERR_OUT_OF_MEMORY, "out of host memory for a tile");
     return 1;
 }
 
@@ -129,21 +152,33 @@ int rm_task_await(rm_task* t, rm_vec3* out) {
     t->cv.wait(lk, [&] { return t->finished; });
     if (t->status != RM_OK) return fail(t->status, t->error);
     const size_t W = t->settings.camera_settings.backbuffer_width, H = t->settings.camera_settings.backbuffer_height;
-    for (size_t i = 0; i < W * H; i++) out[i] = rm_vec3{0.0, 0.0, 0.0};
-    std::deque<rm_message> keep;
+    // drain: TileProgressed messages are skipped, not a stop (the reference breaks at the first one, src/trace.rs:101-103)
+    std::vector<PendingMessage> finished;
     while (!t->messages.empty()) {
-        rm_message m = t->messages.front();
+        if (t->messages.front().kind == RM_TILE_FINISHED) finished.push_back(std::move(t->messages.front()));
         t->messages.pop_front();
-        if (m.kind != RM_TILE_FINISHED) { rm_tile_free(&m.tile); continue; }   // skipped, not a stop (the reference breaks here)
-        const rm_tile& tile = m.tile;
-        const double c = (double)tile.sample_count;
-        for (size_t y = 0; y < tile.height; y++)
-            for (size_t x = 0; x < tile.width; x++) {
-                const rm_vec3& v = tile.data[x + y * tile.width];
-                out[x + tile.left + (y + tile.top) * W] = rm_vec3{v.x / c, v.y / c, v.z / c};   // src/trace.rs:95-97
-            }
-        rm_tile_free(&m.tile);
     }
+    lk.unlock();
+    // out[x + left + (y + top) * W] = tile.data[..] / tile.sample_count as f64      src/trace.rs:95-97 — pixels no finished tile
+    // covers (another rank's tiles) stay zero; rows are divided by a few host threads
+    auto rows = [&](size_t y0, size_t y1) {
+        for (size_t y = y0; y < y1; y++) memset((void*)(out + y * W), 0, W * sizeof(rm_vec3));
+        for (const PendingMessage& m : finished) {
+            const double c = (double)m.sample_count;
+            const size_t a = std::max(y0, m.rect.top), b = std::min(y1, m.rect.top + m.rect.height);
+            for (size_t y = a; y < b; y++) {
+                const rm_vec3* src = m.frame->sums.data() + y * m.frame->W + m.rect.left;
+                rm_vec3* dst = out + y * W + m.rect.left;
+                for (size_t x = 0; x < m.rect.width; x++) dst[x] = rm_vec3{src[x].x / c, src[x].y / c, src[x].z / c};
+            }
+        }
+    };
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t workers = W * H < ((size_t)1 << 18) ? 1 : std::min<size_t>(hw ? hw : 4, 8);
+    std::vector<std::thread> pool;
+    for (size_t w = 1; w < workers; w++) pool.emplace_back(rows, H * w / workers, H * (w + 1) / workers);
+    rows(0, H / workers);
+    for (std::thread& th : pool) th.join();
     return RM_OK;
 }
 
@@ -160,19 +195,21 @@ int rm_task_pump(rm_task* t) {
     if (!t) return fail(RM_ERR_INVALID_ARGUMENT, "rm_task_pump: null task");
     int delivered = 0;
     for (;;) {
-        rm_message m;
+        PendingMessage m;
         rm_tile_callback cb;
         void* user;
         {
             std::lock_guard<std::mutex> lk(t->mu);
             if (t->messages.empty() || t->messages.front().kind != RM_TILE_PROGRESSED) break;
-            m = t->messages.front();
+            m = std::move(t->messages.front());
             t->messages.pop_front();
             cb = t->callback;
             user = t->callback_user;
         }
-        if (cb) cb(&m.tile, user);
-        rm_tile_free(&m.tile);
+        rm_tile tile{};
+        if (!make_tile(m, &tile)) return fail(RM_ERR_OUT_OF_MEMORY, "out of host memory for a tile");
+        if (cb) cb(&tile, user);
+        rm_tile_free(&tile);
         delivered++;
     }
     return delivered;
@@ -195,7 +232,6 @@ int rm_task_stats(rm_task* t, rm_stats* out) {
 void rm_task_destroy(rm_task* t) {
     if (!t) return;
     if (t->driver.joinable()) t->driver.join();
-    for (rm_message& m : t->messages) rm_tile_free(&m.tile);
     rm_renderer_destroy(t->renderer);
     delete t;
 }
