@@ -471,10 +471,10 @@ static int renderer_init(rm_renderer* r) {
     // batch: enough paths in flight to fill the machine many times over, bounded in memory
     size_t spp = r->opt.batch_spp;
     if (spp == 0) {
-        // ~32 Mi paths per wavefront batch: the deep stages of a batch hold few rays, and every stage ends with the tail
-        // of a persistent kernel, so bigger batches amortise both (measured: 4 -> 16 spp at 1080p is +9 %).  328 B of
+        // ~64 Mi paths per wavefront batch: the deep stages of a batch hold few rays, and every stage ends with the tail
+        // of a persistent kernel, so bigger batches amortise both (measured at 1080p: 4 -> 16 spp +9 %, 16 -> 32 spp +1.6 %).  328 B of
         // queues per path; never more than a quarter of the free device memory.
-        size_t target = (size_t)32 << 20;
+        size_t target = (size_t)64 << 20;
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) target = std::min(target, std::max<size_t>(free_b / 4 / 328, (size_t)1 << 20));
         spp = npix ? std::max<size_t>(1, target / npix) : 1;
