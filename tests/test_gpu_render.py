@@ -193,3 +193,24 @@ def test_missing_device_is_an_error_not_a_fallback():
         sc.intersect(np.array([[0, 0, 0, 0, 0, 1.0]]), device=99)
     with pytest.raises(A.RaymondError):
         A.Renderer(sc, settings(F.camera(8, 8), 1), A.GpuOptions(device=99))
+
+
+def test_cuda_render_against_the_reference_own_image():
+    """The CUDA path against the only output of the reference itself: examples/ReflectiveSpheres.png (592x340, 500 spp,
+    block means committed under tests/golden/).  Same bounds as the oracle's own test (tests/test_oracle.py): the difference
+    is Monte-Carlo noise — block-mean |diff| <= 0.30 of 255 levels, image means within 0.15, the ceiling exactly 227."""
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_png_blocks.json")))["ReflectiveSpheres"]
+    W, H, spp, B = gold["width"], gold["height"], 500, gold["block"]
+    r = A.Renderer(product_scene(F.reflective_spheres()), settings(F.camera(W, H), spp), A.GpuOptions(seed=2024))
+    r.render(0, spp)
+    img = r.read_rgb8(spp)                      # the GPU tonemap epilogue (cli_old/src/main.rs:157-181)
+    stats = r.stats()
+    r.close()
+    assert stats["nonfinite_samples"] == 0
+    assert np.abs(img.reshape(-1, 3).mean(axis=0) - np.array(gold["image_mean_rgb8"])).max() <= 0.15
+    blocks = img[:H // B * B, :W // B * B].astype(np.float64).reshape(H // B, B, W // B, B, 3).mean(axis=(1, 3))
+    bd = np.abs(blocks - np.array(gold["mean_rgb8"]))
+    assert bd.mean() <= 0.30 and np.percentile(bd, 95) <= 0.85 and bd.max() <= 2.5, (bd.mean(), np.percentile(bd, 95), bd.max())
+    assert img[10, 296].tolist() == gold["ceiling_pixel_296_10"]
