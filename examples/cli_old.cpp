@@ -24,6 +24,7 @@ int main(int argc, char** argv) {
     const char* mesh_path = nullptr;
     const char* out_path = "output.png";
     unsigned long long seed = 0;
+    unsigned gpus = 1;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--mesh") && i + 1 < argc) mesh_path = argv[++i];
         else if (!strcmp(argv[i], "--out") && i + 1 < argc) out_path = argv[++i];
@@ -31,7 +32,8 @@ int main(int argc, char** argv) {
         else if (!strcmp(argv[i], "--height") && i + 1 < argc) height = strtoull(argv[++i], nullptr, 10);
         else if (!strcmp(argv[i], "--spp") && i + 1 < argc) spp = strtoull(argv[++i], nullptr, 10);
         else if (!strcmp(argv[i], "--seed") && i + 1 < argc) seed = strtoull(argv[++i], nullptr, 10);
-        else { fprintf(stderr, "usage: cli_old [--mesh dragon.ply] [--out output.png] [--width W --height H --spp N --seed S]\n"); return 2; }
+        else if (!strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = (unsigned)strtoul(argv[++i], nullptr, 10);
+        else { fprintf(stderr, "usage: cli_old [--mesh dragon.ply] [--out output.png] [--width W --height H --spp N --seed S --gpus G]\n"); return 2; }
     }
     const auto now = std::chrono::steady_clock::now();
 
@@ -73,6 +75,7 @@ int main(int argc, char** argv) {
     settings.worker_count = 0;
     rm_gpu_options opt{};
     opt.seed = seed;
+    opt.device_count = gpus;                 // > 1: the samples are split over that many GPUs of this box
 
     rm_task* task = rm_render_tiled(scene, &settings, &opt);                                  // :152
     if (!task) { fprintf(stderr, "render_tiled: %s\n", rm_last_error()); return 1; }

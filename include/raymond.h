@@ -218,7 +218,9 @@ typedef struct rm_gpu_options {
     void* accum_device;      /* optional caller-owned device buffer, W*H rm_vec3 (f64 sums), zeroed by the library */
     size_t batch_spp;        /* samples per pixel per wavefront batch; 0 = auto */
     uint32_t flags;          /* RM_FLAG_* */
-    uint32_t reserved;
+    uint32_t device_count;   /* rm_render_tiled only: > 1 renders on devices device .. device+device_count-1 from THIS process (one
+                              * driver thread and stream per GPU, `partition` between them) and sums the accumulators onto the first
+                              * device with peer copies over NVLink.  rank / world_size are then set by the library.  0 or 1 = one GPU. */
 } rm_gpu_options;
 
 /* Tile { sample_count, width, height, left, top, data }   core/src/tile.rs:6-14

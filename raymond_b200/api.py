@@ -82,7 +82,7 @@ class SettingsC(C.Structure):
 
 class GpuOptionsC(C.Structure):
     _fields_ = [("device", C.c_int32), ("rank", C.c_int32), ("world_size", C.c_int32), ("partition", C.c_uint32), ("seed", C.c_uint64),
-                ("stream", C.c_void_p), ("accum_device", C.c_void_p), ("batch_spp", C.c_size_t), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+                ("stream", C.c_void_p), ("accum_device", C.c_void_p), ("batch_spp", C.c_size_t), ("flags", C.c_uint32), ("device_count", C.c_uint32)]
 
 
 class TileC(C.Structure):
@@ -482,10 +482,11 @@ class GpuOptions:
     accum_device: int = 0
     batch_spp: int = 0
     flags: int = 0
+    device_count: int = 0     # render_tiled only: > 1 = that many GPUs driven from this process
 
     def _c(self) -> GpuOptionsC:
         return GpuOptionsC(self.device, self.rank, self.world_size, self.partition, self.seed, self.stream or None, self.accum_device or None,
-                           self.batch_spp, self.flags, 0)
+                           self.batch_spp, self.flags, self.device_count)
 
 
 def tile_layout(settings: Settings) -> np.ndarray:

@@ -608,6 +608,50 @@ static void harvest_events(rm_renderer* r) {
 
 }  // namespace rm
 
+namespace rm {
+
+__global__ void __launch_bounds__(256) k_add(double* __restrict__ total, const double* __restrict__ part, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) total[i] += part[i];
+}
+
+int reduce_accumulators_to_host(rm_renderer* const* rs, int count, rm_vec3* out) {
+    if (count <= 0 || !rs || !out) return fail(RM_ERR_INVALID_ARGUMENT, "reduce_accumulators_to_host: bad argument");
+    rm_renderer* r0 = rs[0];
+    const size_t n = r0->settings.camera_settings.backbuffer_width * r0->settings.camera_settings.backbuffer_height * 3;
+    for (int g = 1; g < count; g++) {            // everything the peers rendered must be complete before it is copied
+        RM_CUDA(cudaSetDevice(rs[g]->device));
+        RM_CUDA(cudaStreamSynchronize(rs[g]->stream));
+    }
+    RM_CUDA(cudaSetDevice(r0->device));
+    if (count == 1) {
+        RM_CUDA(cudaMemcpyAsync(out, r0->accum, n * sizeof(double), cudaMemcpyDeviceToHost, r0->stream));
+        RM_CUDA(cudaStreamSynchronize(r0->stream));
+        return RM_OK;
+    }
+    double *total = nullptr, *part = nullptr;
+    RM_CUDA(dev_malloc(&total, n * sizeof(double)));
+    RM_CUDA(dev_malloc(&part, n * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(total, r0->accum, n * sizeof(double), cudaMemcpyDeviceToDevice, r0->stream);
+    for (int g = 1; g < count && e == cudaSuccess; g++) {
+        cudaDeviceEnablePeerAccess(rs[g]->device, 0);        // NVLink P2P when available; the copy works either way
+        cudaGetLastError();
+        e = cudaMemcpyPeerAsync(part, r0->device, rs[g]->accum, rs[g]->device, n * sizeof(double), r0->stream);
+        if (e == cudaSuccess) {
+            k_add<<<(unsigned)std::min<size_t>((n + 255) / 256, (size_t)r0->sms * 16), 256, 0, r0->stream>>>(total, part, n);
+            r0->launches++;
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, total, n * sizeof(double), cudaMemcpyDeviceToHost, r0->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(r0->stream);
+    dev_free(total);
+    dev_free(part);
+    if (e != cudaSuccess) return fail(RM_ERR_CUDA, std::string("accumulator reduce: ") + cudaGetErrorString(e));
+    return RM_OK;
+}
+
+}  // namespace rm
+
 // ===================================================================== C ABI (device level)
 
 extern "C" {

@@ -13,6 +13,8 @@
 
 #include "../../include/raymond.h"
 
+struct rm_renderer;
+
 namespace rm {
 
 void set_error(const std::string& msg);
@@ -64,6 +66,9 @@ std::vector<TileRect> tile_layout(size_t W, size_t H, size_t tw, size_t th);
 void* pinned_acquire(size_t bytes);
 void pinned_release(void* p);
 // Device memory from the cached stream-ordered pool (rm_device.cu); dev_alloc returns a cudaError_t value (0 = ok).
+// Sum of the accumulators of several renderers (one per device) into pinned host memory: peer copies onto the first
+// renderer's device + an add kernel per peer, in renderer order (rm_device.cu).  Synchronises every renderer's stream.
+int reduce_accumulators_to_host(rm_renderer* const* renderers, int count, rm_vec3* out_pinned);
 // display transform kernel (rm_display.cu): sums / divisor -> tonemap -> 8-bit RGB, device pointers
 int tonemap_device(const double* sums_device, size_t n_pixels, double divisor, double exposure, double gamma, unsigned char* out_device, void* stream);
 int dev_alloc(void** p, size_t bytes);

@@ -28,7 +28,7 @@ struct PendingMessage {
 struct rm_task {
     rm_settings settings{};
     rm_gpu_options options{};
-    rm_renderer* renderer = nullptr;
+    std::vector<rm_renderer*> renderers;     // one per GPU (options.device_count), in rank order
     std::thread driver;
     std::mutex mu;
     std::condition_variable cv;
@@ -72,15 +72,24 @@ void post_tiles(rm_task* t, uint32_t kind, size_t sample_count, const rm_vec3* s
     t->cv.notify_all();
 }
 
+// global sample indices in [begin, end) that rank g of G renders under the sample partition: first, count (stride G)
+void sample_share(size_t begin, size_t end, size_t g, size_t G, size_t* first, size_t* count) {
+    const size_t f = begin + ((g + G - begin % G) % G);
+    *first = f;
+    *count = f < end ? (end - f + G - 1) / G : 0;
+}
+
 void drive(rm_task* t) {
     const rm_settings& s = t->settings;
     const size_t W = s.camera_settings.backbuffer_width, H = s.camera_settings.backbuffer_height;
-    const size_t world = t->options.world_size > 1 ? (size_t)t->options.world_size : 1;
+    const size_t G = t->renderers.size();                 // GPUs driven by this task
+    // a task that is itself one rank of a multi-process job (options.world_size) renders only its share
+    const size_t world = G > 1 ? 1 : (t->options.world_size > 1 ? (size_t)t->options.world_size : 1);
     const bool split_samples = world > 1 && t->options.partition == RM_PARTITION_SAMPLES;
-    // this rank's passes: global samples first, first + stride, ...
     const size_t first = split_samples ? (size_t)t->options.rank : 0;
     const size_t stride = split_samples ? world : 1;
     const size_t total = split_samples ? (s.sample_count > first ? (s.sample_count - first + world - 1) / world : 0) : s.sample_count;
+    const bool split_local = G > 1 && t->options.partition == RM_PARTITION_SAMPLES;
     int st = RM_OK;
     // the frame of running sums lands in a pinned block (cached across tasks): D2H at link speed
     rm_vec3* sums = (rm_vec3*)pinned_acquire(std::max<size_t>(W * H, 1) * sizeof(rm_vec3));
@@ -91,21 +100,38 @@ void drive(rm_task* t) {
         size_t done = 0;
         while (done < total && st == RM_OK) {
             const size_t n = std::min(chunk, total - done);
-            st = rm_renderer_render(t->renderer, first + done * stride, n, stride);
+            if (G == 1) {
+                st = rm_renderer_render(t->renderers[0], first + done * stride, n, stride);
+            } else {
+                // every GPU gets its share of the samples [done, done + n) (or all of them for its own tiles); launches are
+                // asynchronous, so one host thread keeps all devices busy
+                for (size_t g = 0; g < G && st == RM_OK; g++) {
+                    size_t f = done, c = n;
+                    if (split_local) sample_share(done, done + n, g, G, &f, &c);
+                    if (c) st = rm_renderer_render(t->renderers[g], f, c, split_local ? G : 1);
+                }
+            }
             done += n;
             if (st == RM_OK && done < total) {
-                st = rm_renderer_read_sums(t->renderer, sums);
+                st = reduce_accumulators_to_host(t->renderers.data(), (int)G, sums);
                 if (st == RM_OK) post_tiles(t, RM_TILE_PROGRESSED, done, sums);
             }
         }
-        if (st == RM_OK) st = rm_renderer_read_sums(t->renderer, sums);
+        if (st == RM_OK) st = reduce_accumulators_to_host(t->renderers.data(), (int)G, sums);
         if (st == RM_OK) post_tiles(t, RM_TILE_FINISHED, total, sums);      // src/trace.rs:211-212
     } catch (const std::bad_alloc&) {
         st = fail(RM_ERR_OUT_OF_MEMORY, "out of host memory in the render driver");
     }
     pinned_release(sums);
     rm_stats stats{};
-    rm_renderer_stats(t->renderer, &stats);
+    for (size_t g = 0; g < G; g++) {
+        rm_stats one{};
+        rm_renderer_stats(t->renderers[g], &one);
+        stats.samples += one.samples; stats.rays += one.rays; stats.nonfinite_samples += one.nonfinite_samples;
+        stats.kernel_launches += one.kernel_launches; stats.upload_bytes += one.upload_bytes;
+        stats.device_ms = std::max(stats.device_ms, one.device_ms);
+        stats.upload_ms = std::max(stats.upload_ms, one.upload_ms);
+    }
     std::lock_guard<std::mutex> lk(t->mu);
     t->stats = stats;
     t->status = st;
@@ -123,10 +149,37 @@ rm_task* rm_render_tiled(const rm_scene* scene, const rm_settings* settings, con
     rm_task* t = new rm_task();
     t->settings = *settings;
     if (options) t->options = *options;
-    // scene upload happens here, on the caller's thread, so a bad scene or a missing GPU is
-    // reported synchronously; the device copy is the snapshot (the caller may destroy `scene`)
-    t->renderer = rm_renderer_create(scene, settings, options);
-    if (!t->renderer) { delete t; return nullptr; }
+    const size_t G = t->options.device_count > 1 ? t->options.device_count : 1;
+    if (G > 1 && (t->options.world_size > 1 || t->options.stream || t->options.accum_device)) {
+        fail(RM_ERR_INVALID_ARGUMENT, "rm_render_tiled: device_count > 1 excludes world_size, stream and accum_device (they describe one device)");
+        delete t;
+        return nullptr;
+    }
+    // scene upload happens here, before the call returns, so a bad scene or a missing GPU is reported synchronously;
+    // the device copies are the snapshot (the caller may destroy `scene`).  One host thread per GPU flattens and uploads.
+    t->renderers.assign(G, nullptr);
+    std::vector<int> status(G, RM_OK);
+    std::vector<std::string> errors(G);
+    auto create = [&](size_t g) {
+        rm_gpu_options o = t->options;
+        if (G > 1) { o.device = t->options.device + (int32_t)g; o.rank = (int32_t)g; o.world_size = (int32_t)G; }
+        o.device_count = 0;
+        t->renderers[g] = rm_renderer_create(scene, settings, &o);
+        if (!t->renderers[g]) { status[g] = rm_last_status(); errors[g] = rm_last_error(); }
+    };
+    {
+        std::vector<std::thread> pool;
+        for (size_t g = 1; g < G; g++) pool.emplace_back(create, g);
+        create(0);
+        for (std::thread& th : pool) th.join();
+    }
+    for (size_t g = 0; g < G; g++)
+        if (!t->renderers[g]) {
+            for (rm_renderer* r : t->renderers) rm_renderer_destroy(r);
+            fail(status[g] ? status[g] : RM_ERR_CUDA, errors[g]);
+            delete t;
+            return nullptr;
+        }
     t->driver = std::thread(drive, t);
     return t;
 }
@@ -232,7 +285,7 @@ int rm_task_stats(rm_task* t, rm_stats* out) {
 void rm_task_destroy(rm_task* t) {
     if (!t) return;
     if (t->driver.joinable()) t->driver.join();
-    rm_renderer_destroy(t->renderer);
+    for (rm_renderer* r : t->renderers) rm_renderer_destroy(r);
     delete t;
 }
 
