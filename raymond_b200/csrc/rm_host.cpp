@@ -10,6 +10,7 @@
 #include <cstring>
 #include <fstream>
 #include <limits>
+#include <thread>
 
 #include "rm_internal.hpp"
 
@@ -239,48 +240,105 @@ int load_ply(const char* path, Mesh* mesh) {
     }
     (void)header_done;   // a header without end_header just leaves no lines for the vertex loop
 
-    std::vector<rm_vertex> vertices;
-    vertices.reserve(n_vertices);
-    for (size_t i = 0; i < n_vertices; i++) {
-        if (!lr.next(&b, &e)) return fail(RM_ERR_PLY, "PLY ends inside the vertex list (mesh.rs:81 unwrap)");
-        double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        int k = 0;
-        while (token(b, e, &tb, &te)) {
-            double x;
-            if (!parse_f64(tb, te, &x)) return fail(RM_ERR_PLY, "vertex line " + std::to_string(i) + " holds a non-number (mesh.rs:83 unwrap)");
-            if (k < 8) v[k] = x;
-            k++;
-        }
-        if (k < 6) return fail(RM_ERR_PLY, "vertex line " + std::to_string(i) + " has fewer than 6 numbers (mesh.rs:85-86 index)");
-        rm_vertex vx;
-        vx.position = rm_vec3{v[0], v[1], v[2]};
-        vx.normal = rm_vec3{v[3], v[4], v[5]};
-        vx.uv = rm_vec2{k > 6 ? v[6] : 0.0, k > 7 ? v[7] : 0.0};
-        vx.tangent = rm_vec3{0.0, 0.0, 0.0};
-        vertices.push_back(vx);
+    // The body is parsed by a few host threads: line starts are collected in one pass, vertex lines and face lines are
+    // independent of each other (a face's tangent is computed from the three vertices' positions and uvs and stored in
+    // ITS copies of them, mesh.rs:101-114).  The first failure in line order is the one reported, as a sequential reader would.
+    std::vector<std::pair<const char*, const char*>> lines;
+    lines.reserve((size_t)(lr.end - lr.p) / 24 + 16);
+    while (lr.next(&b, &e)) lines.emplace_back(b, e);
+    const size_t n_vlines = std::min(n_vertices, lines.size());
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t workers = lines.size() < 20000 ? 1 : std::min<size_t>(hw ? hw : 4, 16);
+    struct Failure { size_t line = (size_t)-1; std::string msg; };
+    auto first_failure = [](const std::vector<Failure>& f) { size_t best = 0; for (size_t i = 1; i < f.size(); i++) if (f[i].line < f[best].line) best = i; return f[best]; };
+
+    std::unique_ptr<rm_vertex[]> vertices(new rm_vertex[std::max<size_t>(n_vlines, 1)]);   // first touched by the parsing threads
+    {
+        std::vector<Failure> fails(workers);
+        auto parse_vertices = [&](size_t w) {
+            const char *tb, *te;
+            for (size_t i = n_vlines * w / workers; i < n_vlines * (w + 1) / workers; i++) {
+                const char* b = lines[i].first;
+                const char* e = lines[i].second;
+                double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                int k = 0;
+                while (token(b, e, &tb, &te)) {
+                    double x;
+                    if (!parse_f64(tb, te, &x)) { fails[w] = Failure{i, "vertex line " + std::to_string(i) + " holds a non-number (mesh.rs:83 unwrap)"}; return; }
+                    if (k < 8) v[k] = x;
+                    k++;
+                }
+                if (k < 6) { fails[w] = Failure{i, "vertex line " + std::to_string(i) + " has fewer than 6 numbers (mesh.rs:85-86 index)"}; return; }
+                rm_vertex& vx = vertices[i];
+                vx.position = rm_vec3{v[0], v[1], v[2]};
+                vx.normal = rm_vec3{v[3], v[4], v[5]};
+                vx.uv = rm_vec2{k > 6 ? v[6] : 0.0, k > 7 ? v[7] : 0.0};
+                vx.tangent = rm_vec3{0.0, 0.0, 0.0};
+            }
+        };
+        std::vector<std::thread> pool;
+        for (size_t w = 1; w < workers; w++) pool.emplace_back(parse_vertices, w);
+        parse_vertices(0);
+        for (std::thread& t : pool) t.join();
+        const Failure f = first_failure(fails);
+        if (f.line != (size_t)-1) return fail(RM_ERR_PLY, f.msg);
+        if (lines.size() < n_vertices) return fail(RM_ERR_PLY, "PLY ends inside the vertex list (mesh.rs:81 unwrap)");
     }
 
     std::vector<rm_triangle> faces;
-    while (lr.next(&b, &e)) {
-        uint32_t idx[4];
-        int k = 0;
-        while (token(b, e, &tb, &te)) {
-            uint32_t x;
-            if (!parse_u32(tb, te, &x)) return fail(RM_ERR_PLY, "face line holds a non-u32 token (mesh.rs:95 unwrap)");
-            if (k < 4) idx[k] = x;
-            k++;
+    {
+        const size_t n_flines = lines.size() - n_vlines;
+        std::vector<Failure> fails(workers);
+        struct Tri { uint32_t a, b, c; };
+        std::vector<std::vector<Tri>> part(workers);
+        auto parse_faces = [&](size_t w) {
+            const char *tb, *te;
+            std::vector<Tri>& out = part[w];
+            const size_t lo = n_flines * w / workers, hi = n_flines * (w + 1) / workers;
+            out.reserve(hi - lo);
+            for (size_t i = lo; i < hi; i++) {
+                const char* b = lines[n_vlines + i].first;
+                const char* e = lines[n_vlines + i].second;
+                uint32_t idx[4];
+                int k = 0;
+                while (token(b, e, &tb, &te)) {
+                    uint32_t x;
+                    if (!parse_u32(tb, te, &x)) { fails[w] = Failure{i, "face line holds a non-u32 token (mesh.rs:95 unwrap)"}; return; }
+                    if (k < 4) idx[k] = x;
+                    k++;
+                }
+                if (k == 0) { fails[w] = Failure{i, "empty line in the face list (mesh.rs:97 index)"}; return; }
+                if (idx[0] != 3) continue;                          // non-triangles are silently dropped (mesh.rs:116)
+                if (k < 4) { fails[w] = Failure{i, "triangle face with fewer than 3 indices"}; return; }
+                for (int j = 1; j <= 3; j++)
+                    if (idx[j] >= n_vlines) { fails[w] = Failure{i, "face index out of range (mesh.rs:102-104 index)"}; return; }
+                out.push_back(Tri{idx[1], idx[2], idx[3]});
+            }
+        };
+        {
+            std::vector<std::thread> pool;
+            for (size_t w = 1; w < workers; w++) pool.emplace_back(parse_faces, w);
+            parse_faces(0);
+            for (std::thread& t : pool) t.join();
         }
-        if (k == 0) return fail(RM_ERR_PLY, "empty line in the face list (mesh.rs:97 index)");
-        if (idx[0] != 3) continue;                          // non-triangles are silently dropped (mesh.rs:116)
-        if (k < 4) return fail(RM_ERR_PLY, "triangle face with fewer than 3 indices");
-        for (int j = 1; j <= 3; j++)
-            if (idx[j] >= vertices.size()) return fail(RM_ERR_PLY, "face index out of range (mesh.rs:102-104 index)");
-        // the face's tangent is written into the shared vertices before they are copied (mesh.rs:101-114)
-        rm_vec3 tg = face_tangent(vertices[idx[1]], vertices[idx[2]], vertices[idx[3]]);
-        vertices[idx[1]].tangent = tg;
-        vertices[idx[2]].tangent = tg;
-        vertices[idx[3]].tangent = tg;
-        faces.push_back(rm_triangle{vertices[idx[1]], vertices[idx[2]], vertices[idx[3]]});
+        const Failure f = first_failure(fails);
+        if (f.line != (size_t)-1) return fail(RM_ERR_PLY, f.msg);
+        std::vector<size_t> offset(workers + 1, 0);
+        for (size_t w = 0; w < workers; w++) offset[w + 1] = offset[w] + part[w].size();
+        faces.resize(offset[workers]);
+        auto build = [&](size_t w) {
+            for (size_t i = 0; i < part[w].size(); i++) {
+                const Tri& x = part[w][i];
+                rm_triangle& t = faces[offset[w] + i];
+                t = rm_triangle{vertices[x.a], vertices[x.b], vertices[x.c]};
+                const rm_vec3 tg = face_tangent(t.v0, t.v1, t.v2);       // the face's tangent goes into its copies of the vertices
+                t.v0.tangent = tg; t.v1.tangent = tg; t.v2.tangent = tg;
+            }
+        };
+        std::vector<std::thread> pool;
+        for (size_t w = 1; w < workers; w++) pool.emplace_back(build, w);
+        build(0);
+        for (std::thread& t : pool) t.join();
     }
     mesh->triangles = std::move(faces);
     mesh->bounds = mesh_bounds(mesh->triangles.data(), mesh->triangles.size());
