@@ -24,7 +24,7 @@ int main(int argc, char** argv) {
     const char* mesh_path = nullptr;
     const char* out_path = "output.png";
     unsigned long long seed = 0;
-    unsigned gpus = 1;
+    unsigned gpus = 1, repeat = 1;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--mesh") && i + 1 < argc) mesh_path = argv[++i];
         else if (!strcmp(argv[i], "--out") && i + 1 < argc) out_path = argv[++i];
@@ -33,9 +33,13 @@ int main(int argc, char** argv) {
         else if (!strcmp(argv[i], "--spp") && i + 1 < argc) spp = strtoull(argv[++i], nullptr, 10);
         else if (!strcmp(argv[i], "--seed") && i + 1 < argc) seed = strtoull(argv[++i], nullptr, 10);
         else if (!strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = (unsigned)strtoul(argv[++i], nullptr, 10);
-        else { fprintf(stderr, "usage: cli_old [--mesh dragon.ply] [--out output.png] [--width W --height H --spp N --seed S --gpus G]\n"); return 2; }
+        else if (!strcmp(argv[i], "--repeat") && i + 1 < argc) repeat = (unsigned)strtoul(argv[++i], nullptr, 10);
+        else { fprintf(stderr, "usage: cli_old [--mesh dragon.ply] [--out output.png] [--width W --height H --spp N --seed S --gpus G --repeat R]\n"); return 2; }
     }
     const auto now = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {       // phase times on stderr (the reference prints only the total)
+        fprintf(stderr, "[cli_old] %-28s %.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - now).count());
+    };
 
     rm_scene* scene = rm_scene_create();
     rm_material m = diffuse(1.0, 0.0, 0.0, 0.02);
@@ -43,10 +47,12 @@ int main(int argc, char** argv) {
     if (mesh_path) {
         rm_mesh* mesh = rm_mesh_load_ply(mesh_path);                                          // :60
         if (!mesh) { fprintf(stderr, "load_ply: %s\n", rm_last_error()); return 1; }
+        lap("load_ply");
         CHECK(rm_mesh_translate(mesh, {0.0, -0.3, 2.9}));                                     // :61
         int st = RM_OK;
         rm_grid* grid = rm_grid_build(mesh, &st);                                             // :62 AccGrid::build_from_mesh
         rm_mesh_destroy(mesh);
+        lap("bake_transform + build grid");
         if (!grid) { fprintf(stderr, "build_from_mesh: %s\n", rm_last_error()); return 1; }
         m = metal(1.0, 1.0, 0.1, 0.15);
         CHECK(rm_scene_add_grid(scene, grid, &m));                                            // :70-75
@@ -77,19 +83,31 @@ int main(int argc, char** argv) {
     opt.seed = seed;
     opt.device_count = gpus;                 // > 1: the samples are split over that many GPUs of this box
 
-    rm_task* task = rm_render_tiled(scene, &settings, &opt);                                  // :152
-    if (!task) { fprintf(stderr, "render_tiled: %s\n", rm_last_error()); return 1; }
-    rm_scene_destroy(scene);                                                                  // the library snapshotted it
+    // --repeat R renders the frame R times in this process: the first one pays CUDA's one-time start-up (a context per GPU)
     std::vector<rm_vec3> render(width * height);
-    CHECK(rm_task_await(task, render.data()));                                                // :153
     rm_stats stats{};
-    rm_task_stats(task, &stats);
-    rm_task_destroy(task);
+    for (unsigned rep = 0; rep < (repeat ? repeat : 1); rep++) {
+        const auto r0 = std::chrono::steady_clock::now();
+        opt.seed = seed + rep;
+        rm_task* task = rm_render_tiled(scene, &settings, &opt);                              // :152
+        if (!task) { fprintf(stderr, "render_tiled: %s\n", rm_last_error()); return 1; }
+        lap("render_tiled returned");
+        CHECK(rm_task_await(task, render.data()));                                            // :153
+        lap("await returned");
+        rm_task_stats(task, &stats);
+        rm_task_destroy(task);
+        fprintf(stderr, "[cli_old] frame %u: render_tiled + await %.3f s (device %.1f ms)\n", rep,
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - r0).count(), stats.device_ms);
+    }
+    rm_scene_destroy(scene);
 
     std::vector<uint8_t> export_(width * height * 3);
     CHECK(rm_tonemap_rgb8(render.data(), width * height, 1.0, 2.2, 0, export_.data()));       // :157-181
+    lap("tonemap");
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - now).count();
     printf("Finished render.\nTotal render time: %.3fs\nTotal amount of trace calls: %llu\n", secs, (unsigned long long)stats.rays);   // :183-188
     CHECK(rm_write_png(out_path, export_.data(), width, height));                             // :194-197
+    lap("png written");
+    fprintf(stderr, "[cli_old] device time %.1f ms, %llu kernel launches, upload %.1f ms\n", stats.device_ms, (unsigned long long)stats.kernel_launches, stats.upload_ms);
     return 0;
 }

@@ -9,6 +9,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "rm_kernels.cuh"
@@ -149,7 +150,8 @@ struct rm_device_scene {
     int traverse_blocks_per_sm = 2;
     DevScene scene{};
     std::vector<int> grid_objects;          // object indices with Geometry::Grid, ascending
-    std::vector<void*> allocations;
+    std::vector<void*> allocations;         // one device block per distinct grid, in DevScene::grid order
+    std::vector<size_t> allocation_bytes;
     std::vector<std::shared_ptr<Grid>> keep;
     double upload_ms = 0.0;
     size_t bytes = 0;
@@ -263,6 +265,7 @@ static int upload_grid(rm_device_scene* ds, const Grid& g, DevGrid* out) {
     cudaError_t e = dev_malloc(&dev, total);
     if (e == cudaSuccess) {
         ds->allocations.push_back(dev);
+        ds->allocation_bytes.push_back(total);
         ds->bytes += total;
         e = cudaMemcpyAsync(dev, host, total, cudaMemcpyHostToDevice, 0);
         if (e == cudaSuccess) e = cudaStreamSynchronize(0);      // the staging block goes back to the pool on return
@@ -672,6 +675,68 @@ rm_device_scene* rm_device_scene_create(const rm_scene* scene, int device) {
 }
 
 void rm_device_scene_destroy(rm_device_scene* ds) { delete ds; }
+
+/* The same scene on another device of this process: the grid blocks are copied device to device (NVLink peer copy)
+ * instead of being flattened, staged and uploaded from the host again. */
+rm_device_scene* rm_device_scene_clone_to(const rm_device_scene* src, int device) {
+    if (!src) { fail(RM_ERR_INVALID_ARGUMENT, "rm_device_scene_clone_to: null scene"); return nullptr; }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        fail(RM_ERR_CUDA, "no usable CUDA device " + std::to_string(device) + "; this library has no CPU path");
+        return nullptr;
+    }
+    rm_device_scene* ds = new rm_device_scene();
+    ds->device = device;
+    ds->scene = src->scene;
+    ds->grid_objects = src->grid_objects;
+    ds->keep = src->keep;
+    cudaError_t e = cudaSetDevice(device);
+    ds->sms = sm_count(device);
+    ds->traverse_blocks_per_sm = src->traverse_blocks_per_sm;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    if (e == cudaSuccess) e = cudaEventRecord(e0, 0);
+    for (size_t i = 0; i < src->allocations.size() && e == cudaSuccess; i++) {
+        void* dev = nullptr;
+        e = dev_malloc(&dev, src->allocation_bytes[i]);
+        if (e != cudaSuccess) break;
+        ds->allocations.push_back(dev);
+        ds->allocation_bytes.push_back(src->allocation_bytes[i]);
+        ds->bytes += src->allocation_bytes[i];
+        cudaDeviceEnablePeerAccess(src->device, 0);
+        cudaGetLastError();
+        e = cudaMemcpyPeerAsync(dev, device, src->allocations[i], src->device, src->allocation_bytes[i], 0);
+        // the block keeps its layout: every array pointer moves by the same distance
+        const ptrdiff_t shift = (const char*)dev - (const char*)src->allocations[i];
+        DevGrid& g = ds->scene.grid[i];
+        auto move = [&](auto*& p) { p = (std::remove_reference_t<decltype(p)>)((const char*)p + shift); };
+        move(g.cells); move(g.occ); move(g.refs); move(g.tri); move(g.sphr); move(g.shd);
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(e1, 0);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    ds->upload_ms = ms;
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (e != cudaSuccess) {
+        fail(RM_ERR_CUDA, std::string("rm_device_scene_clone_to: ") + cudaGetErrorString(e));
+        delete ds;
+        return nullptr;
+    }
+    return ds;
+}
+
+/* Renderer that takes ownership of `ds` (destroys it with the renderer). */
+rm_renderer* rm_renderer_create_owning(rm_device_scene* ds, const rm_settings* settings, const rm_gpu_options* options) {
+    rm_renderer* r = rm_renderer_create_on(ds, settings, options);
+    if (r) r->owns_scene = true;
+    return r;
+}
+
+rm_device_scene* rm_renderer_device_scene(rm_renderer* r) { return r ? r->ds : nullptr; }
 
 int rm_device_scene_intersect(rm_device_scene* ds, const rm_ray* rays, size_t count, int64_t* obj, uint64_t* sub, double* distance, void* stream_) {
     if (!ds || (!rays && count)) return fail(RM_ERR_INVALID_ARGUMENT, "rm_device_scene_intersect: null argument");

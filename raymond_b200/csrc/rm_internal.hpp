@@ -76,6 +76,13 @@ void dev_release(void* p);
 
 }  // namespace rm
 
+// internal entry points of rm_device.cu used by the multi-GPU task driver (C linkage, not part of include/raymond.h)
+extern "C" {
+rm_device_scene* rm_device_scene_clone_to(const rm_device_scene* src, int device);
+rm_renderer* rm_renderer_create_owning(rm_device_scene* ds, const rm_settings* settings, const rm_gpu_options* options);
+rm_device_scene* rm_renderer_device_scene(rm_renderer* r);
+}
+
 struct rm_mesh { rm::Mesh mesh; };
 struct rm_grid { std::shared_ptr<rm::Grid> grid; std::atomic<int> refs{1}; };
 struct rm_scene { std::vector<rm::Object> objects; };

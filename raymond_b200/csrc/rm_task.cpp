@@ -156,25 +156,40 @@ rm_task* rm_render_tiled(const rm_scene* scene, const rm_settings* settings, con
         return nullptr;
     }
     // scene upload happens here, before the call returns, so a bad scene or a missing GPU is reported synchronously;
-    // the device copies are the snapshot (the caller may destroy `scene`).  One host thread per GPU flattens and uploads.
+    // the device copies are the snapshot (the caller may destroy `scene`).  The first GPU gets the scene from the host
+    // (flatten + one H2D copy); every other GPU gets a device-to-device copy of it, one host thread per GPU.
     t->renderers.assign(G, nullptr);
     std::vector<int> status(G, RM_OK);
     std::vector<std::string> errors(G);
-    auto create = [&](size_t g) {
+    auto options_for = [&](size_t g) {
         rm_gpu_options o = t->options;
         if (G > 1) { o.device = t->options.device + (int32_t)g; o.rank = (int32_t)g; o.world_size = (int32_t)G; }
         o.device_count = 0;
-        t->renderers[g] = rm_renderer_create(scene, settings, &o);
-        if (!t->renderers[g]) { status[g] = rm_last_status(); errors[g] = rm_last_error(); }
+        return o;
     };
     {
+        rm_gpu_options o = options_for(0);
+        t->renderers[0] = rm_renderer_create(scene, settings, &o);
+        if (!t->renderers[0]) { status[0] = rm_last_status(); errors[0] = rm_last_error(); }
+    }
+    if (t->renderers[0] && G > 1) {
+        rm_device_scene* first = rm_renderer_device_scene(t->renderers[0]);
+        auto create = [&](size_t g) {
+            rm_gpu_options o = options_for(g);
+            rm_device_scene* ds = rm_device_scene_clone_to(first, o.device);
+            if (ds) {
+                t->renderers[g] = rm_renderer_create_owning(ds, settings, &o);
+                if (!t->renderers[g]) rm_device_scene_destroy(ds);
+            }
+            if (!t->renderers[g]) { status[g] = rm_last_status(); errors[g] = rm_last_error(); }
+        };
         std::vector<std::thread> pool;
-        for (size_t g = 1; g < G; g++) pool.emplace_back(create, g);
-        create(0);
+        for (size_t g = 2; g < G; g++) pool.emplace_back(create, g);
+        create(1);
         for (std::thread& th : pool) th.join();
     }
     for (size_t g = 0; g < G; g++)
-        if (!t->renderers[g]) {
+        if (!t->renderers[g] && (g == 0 || t->renderers[0])) {
             for (rm_renderer* r : t->renderers) rm_renderer_destroy(r);
             fail(status[g] ? status[g] : RM_ERR_CUDA, errors[g]);
             delete t;
