@@ -170,6 +170,12 @@ struct rm_device_scene {
 
 namespace rm {
 
+__global__ void __launch_bounds__(256) k_spread_spheres(const float4* __restrict__ per_triangle, const unsigned* __restrict__ refs, size_t n_refs,
+                                                         float4* __restrict__ per_reference) {
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_refs; p += (size_t)gridDim.x * blockDim.x)
+        per_reference[p] = __ldg(&per_triangle[__ldg(&refs[p])]);
+}
+
 // One device allocation + one H2D copy per grid: the flattened arrays are written straight into ONE pinned
 // staging block (cached across calls) laid out like the device block, by a few host threads.
 static int upload_grid(rm_device_scene* ds, const Grid& g, DevGrid* out) {
@@ -184,16 +190,17 @@ static int upload_grid(rm_device_scene* ds, const Grid& g, DevGrid* out) {
     const size_t nc = (size_t)d.n_cells, nt = g.triangles.size(), nr = g.references.size();
     const size_t n_occ = (nc + 31) / 32;
     auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t off_tri = 0, off_sph = off_tri + pad(nt * 12 * sizeof(double)), off_shd = off_sph + pad(nr * sizeof(float4)),
-                 off_cells = off_shd + pad(nt * 18 * sizeof(double)),
+    // device block: [tri][shd][cells][occ][refs][one sphere per triangle] come from the host in one copy; [one sphere per
+    // reference] behind them is spread on the device (k_spread_spheres), so it never crosses the bus
+    const size_t off_tri = 0, off_shd = off_tri + pad(nt * 12 * sizeof(double)), off_cells = off_shd + pad(nt * 18 * sizeof(double)),
                  off_occ = off_cells + pad(nc * sizeof(uint2)), off_refs = off_occ + pad(n_occ * sizeof(unsigned)),
-                 total = off_refs + pad(nr * sizeof(unsigned)) + 256;
-    char* host = (char*)pinned_acquire(total);
-    if (!host) return fail(RM_ERR_OUT_OF_MEMORY, "cannot pin " + std::to_string(total) + " bytes of host staging memory");
+                 off_spht = off_refs + pad(nr * sizeof(unsigned)), host_total = off_spht + pad(nt * sizeof(float4)) + 256,
+                 off_sph = host_total, total = off_sph + pad(nr * sizeof(float4)) + 256;
+    char* host = (char*)pinned_acquire(host_total);
+    if (!host) return fail(RM_ERR_OUT_OF_MEMORY, "cannot pin " + std::to_string(host_total) + " bytes of host staging memory");
     double* tri = (double*)(host + off_tri);
     double* shd = (double*)(host + off_shd);
-    float4* sphr = (float4*)(host + off_sph);          // one sphere per REFERENCE, in reference order
-    std::vector<float4> sph_tri(nt);                     // ... copied from one per triangle
+    float4* sph_tri = (float4*)(host + off_spht);      // one bounding sphere per triangle
     uint2* cells = (uint2*)(host + off_cells);
     unsigned* occ = (unsigned*)(host + off_occ);
     unsigned* refs = (unsigned*)(host + off_refs);
@@ -254,20 +261,19 @@ static int upload_grid(rm_device_scene* ds, const Grid& g, DevGrid* out) {
     fill_cells(0, workers == 1 ? nc : (nc / workers) & ~(size_t)31);
     if (nr) memcpy(refs, g.references.data(), nr * sizeof(unsigned));
     for (std::thread& t : pool) t.join();
-    pool.clear();
-    {
-        auto spread = [&](size_t lo, size_t hi) { for (size_t p = lo; p < hi; p++) sphr[p] = sph_tri[g.references[p]]; };
-        for (size_t w = 1; w < workers; w++) pool.emplace_back(spread, nr * w / workers, nr * (w + 1) / workers);
-        spread(0, nr / workers);
-        for (std::thread& t : pool) t.join();
-    }
     void* dev = nullptr;
     cudaError_t e = dev_malloc(&dev, total);
     if (e == cudaSuccess) {
         ds->allocations.push_back(dev);
         ds->allocation_bytes.push_back(total);
-        ds->bytes += total;
-        e = cudaMemcpyAsync(dev, host, total, cudaMemcpyHostToDevice, 0);
+        ds->bytes += host_total;                                  // bytes that crossed the bus
+        e = cudaMemcpyAsync(dev, host, host_total, cudaMemcpyHostToDevice, 0);
+        if (e == cudaSuccess && nr) {
+            // one sphere per REFERENCE, in reference order: a cell's candidates become one contiguous read for k_traverse
+            k_spread_spheres<<<(unsigned)std::min<size_t>((nr + 255) / 256, (size_t)ds->sms * 32), 256, 0, 0>>>(
+                (const float4*)((char*)dev + off_spht), (const unsigned*)((char*)dev + off_refs), nr, (float4*)((char*)dev + off_sph));
+            e = cudaGetLastError();
+        }
         if (e == cudaSuccess) e = cudaStreamSynchronize(0);      // the staging block goes back to the pool on return
     }
     pinned_release(host);
