@@ -91,3 +91,39 @@ def test_deep_bounce_limit():
     o, oc = O.render(oracle_scene(objs), cam, spp, seed=5, bounce_limit=24)
     compare_same_stream(g, o, spp, "bounce_limit 24", max_outlier_frac=0.02)
     assert gs["rays"] > 0
+
+
+def test_extreme_rays_bit_exact():
+    """Rays a caller may pass to Scene::intersect that stress the conservative pre-test and the DDA set-up: non-unit and tiny /
+    huge directions, far-away origins aimed at the mesh, axis-aligned directions with +0 / -0 components, NaN / Inf inputs."""
+    tris = F.translate(F.bumpy_sphere(40, 80, 1.0, 0.1, (1.0, 0.7, 0.45)), (0.1, -0.2, 3.0))
+    objs = F.soup_scene(tris)
+    rng = np.random.default_rng(12)
+    base = F.random_rays(4000, 31, ((-3.0, 3.0), (-3.0, 3.0), (0.0, 6.0)))
+    target = np.array([0.1, -0.2, 3.0]) + rng.uniform(-0.7, 0.7, size=(4000, 3)) * np.array([1.0, 0.7, 0.45])
+    aimed = base.copy()
+    aimed[:, 3:] = target - aimed[:, :3]                                  # un-normalised directions, |d| ~ 1..6
+    sets = [aimed]
+    for s in (1e-6, 1e-3, 37.5, 1e6, 1e12):
+        r = aimed.copy(); r[:, 3:] *= s; sets.append(r)
+    far = aimed.copy()
+    d = far[:, 3:] / np.linalg.norm(far[:, 3:], axis=1, keepdims=True)
+    for dist in (1e3, 1e6, 1e9):
+        r = far.copy(); r[:, :3] = target - d * dist; r[:, 3:] = d; sets.append(r)
+    axis = np.zeros((600, 6))
+    axis[:, :3] = np.array([0.1, -0.2, 3.0]) + rng.uniform(-0.9, 0.9, size=(600, 3)) * np.array([1.0, 0.7, 0.45])
+    axis[:, 2] -= 4.0
+    axis[:, 5] = 1.0
+    axis[::2, 3] = -0.0; axis[::3, 4] = -0.0
+    sets.append(axis)
+    ax2 = axis.copy(); ax2[:, :3] = axis[:, [2, 0, 1]]; ax2[:, 3:] = axis[:, [5, 3, 4]]; ax2[:, 0] += 4.1; ax2[:, 1] -= 0.3; ax2[:, 2] += 7.2
+    sets.append(ax2)
+    weird = aimed[:64].copy()
+    weird[0, 0] = np.nan; weird[1, 4] = np.nan; weird[2, 3] = np.inf; weird[3, 1] = -np.inf; weird[4, 3:] = 0.0; weird[5, 3:] = (0.0, 0.0, 1e-300)
+    weird[6, :3] = 1e300; weird[7, 3:] = 1e300
+    sets.append(weird)
+    rays = np.ascontiguousarray(np.concatenate(sets))
+    want = oracle_scene(objs).intersect(rays, threads=8)
+    got = product_scene(objs).intersect(rays)
+    assert_hits_equal(got, want, "extreme rays")
+    assert (want[0] >= 0).sum() > 10000
