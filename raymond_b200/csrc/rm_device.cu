@@ -294,7 +294,7 @@ static int build_device_scene(rm_device_scene* ds, const rm_scene* scene) {
     RM_CUDA(cudaSetDevice(ds->device));
     ds->sms = sm_count(ds->device);
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<false>, kBlock, 0) == cudaSuccess && occ > 0) ds->traverse_blocks_per_sm = occ;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<false>, kTravBlock, 0) == cudaSuccess && occ > 0) ds->traverse_blocks_per_sm = occ;
     cudaEvent_t e0, e1;
     RM_CUDA(cudaEventCreate(&e0));
     RM_CUDA(cudaEventCreate(&e1));
@@ -379,8 +379,8 @@ static int launch_intersect(rm_device_scene* ds, const RenderParams& rp, SetupAr
             ta.grid_object = gobj; ta.depth = depth; ta.totals = totals;
             const DevGrid& g = ds->scene.grid[ds->scene.obj[gobj].grid];
             hook.begin(1);
-            if (count_work) k_traverse<true><<<trav_grid, kBlock, 0, stream>>>(g, ta);
-            else k_traverse<false><<<trav_grid, kBlock, 0, stream>>>(g, ta);
+            if (count_work) k_traverse<true><<<trav_grid, kTravBlock, 0, stream>>>(g, ta);
+            else k_traverse<false><<<trav_grid, kTravBlock, 0, stream>>>(g, ta);
             hook.end(1);
         }
     }

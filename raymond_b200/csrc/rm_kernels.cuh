@@ -660,7 +660,11 @@ struct TraverseArgs {
 //      the earliest list position (the reference's strict `<` while walking the list in order)
 //   C  rays with a hit are finished (hit record merged), the others go back to A
 // Idle lanes re-fill from the traversal queue in groups.
-constexpr int kTravWarps = kBlock / 32;
+#ifndef RM_TRAV_BLOCK
+#define RM_TRAV_BLOCK 256
+#endif
+constexpr int kTravBlock = RM_TRAV_BLOCK;          // threads per block of k_traverse
+constexpr int kTravWarps = kTravBlock / 32;
 #ifndef RM_TRAV_MAX_STEPS
 #define RM_TRAV_MAX_STEPS 2
 #endif
@@ -699,7 +703,7 @@ __device__ unsigned long long g_trav_prof[8];
 #endif
 
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(const __grid_constant__ DevGrid g, const __grid_constant__ TraverseArgs a) {
+__global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(const __grid_constant__ DevGrid g, const __grid_constant__ TraverseArgs a) {
     __shared__ TravWarpShared shared[kTravWarps];
     TravWarpShared& sh = shared[threadIdx.x >> 5];
     const unsigned n = *a.n_ptr;
