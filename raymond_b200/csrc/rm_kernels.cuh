@@ -6,9 +6,11 @@
 //   k_setup     one thread per ray: [camera ray generation |  queue read], the analytic objects
 //               (Sphere / Plane), AABB::intersects + DDA set-up of the grid; rays that enter a grid
 //               are appended (ballot/popc compaction) to a traversal queue of 128-byte records
-//   k_traverse  persistent warps over the traversal queue: AccGrid::intersects as a flattened state
-//               machine — each lane does ONE triangle test or ONE cell step per iteration and
-//               re-fills itself from the queue the moment its ray is finished
+//   k_traverse  persistent warps over the traversal queue: AccGrid::intersects in three warp-uniform phases — lanes
+//               walk their ray's DDA four cells ahead to the next occupied cell; the triangle lists of all 32 rays
+//               are pooled, a conservative bounding-sphere pre-test drops the candidates the reference is certain
+//               to reject, and Triangle::intersects runs on the survivors with full lanes; rays with a hit finish,
+//               idle lanes re-fill from the queue in groups
 //   k_shade     one thread per ray: surface normal, material, lobe choice, BRDF weight, next ray or
 //               delivered radiance; survivors are compacted into the next stage's ray queue
 // followed once per batch by k_accumulate (the tile accumulator).
