@@ -347,6 +347,10 @@ int rm_tonemap_rgb8(const rm_vec3* frame_host, size_t pixels, double exposure, d
 /* image.save("output.png")                      cli_old/src/main.rs:194-197: 8-bit RGB PNG (host code). */
 int rm_write_png(const char* path, const uint8_t* rgb8, size_t width, size_t height);
 
+/* The library keeps the device memory of finished renders (a stream-ordered pool per GPU) and its pinned staging blocks
+ * for the next call; this returns them to the driver.  Safe to call at any time no render is in flight. */
+int rm_release_cached_memory(void);
+
 /* Tile rectangles in the reference's queue order (column-major: y advances
  * first, edge tiles clipped — src/trace.rs:142-173).  Returns the tile count;
  * writes min(count, capacity) entries of {left, top, width, height}. */

@@ -130,7 +130,7 @@ ABI_SYMBOLS = [
     "rm_device_scene_intersect", "rm_primary_rays_device", "rm_renderer_create", "rm_renderer_create_on", "rm_renderer_render",
     "rm_renderer_accum_device", "rm_renderer_clear", "rm_renderer_sync", "rm_renderer_read_sums", "rm_renderer_read_frame",
     "rm_renderer_stats", "rm_renderer_stage_stats", "rm_renderer_destroy", "rm_tile_layout", "rm_renderer_read_rgb8", "rm_tonemap_rgb8",
-    "rm_write_png", "rm_project_load_scene", "rm_message_to_json",
+    "rm_write_png", "rm_project_load_scene", "rm_message_to_json", "rm_release_cached_memory",
 ]
 
 _lib = None
@@ -196,6 +196,7 @@ def lib():
         "rm_write_png": (i32, [C.c_char_p, vp, sz, sz]),
         "rm_project_load_scene": (vp, [C.c_char_p, P(i32)]),
         "rm_message_to_json": (sz, [P(MessageC), C.c_char_p, sz]),
+        "rm_release_cached_memory": (i32, []),
         "rm_renderer_stats": (i32, [vp, P(StatsC)]),
         "rm_renderer_stage_stats": (i32, [vp, P(StageStatsC)]),
         "rm_renderer_destroy": (None, [vp]),
@@ -604,6 +605,11 @@ def tonemap(frame: np.ndarray, exposure: float = 1.0, gamma: float = 2.2, device
     out = np.zeros(f.shape, dtype=np.uint8)
     _check(lib().rm_tonemap_rgb8(_ptr(f), f.size // 3, exposure, gamma, device, _ptr(out)))
     return out
+
+
+def release_cached_memory() -> None:
+    """Return the cached device pool and pinned staging blocks to the driver."""
+    _check(lib().rm_release_cached_memory())
 
 
 def write_png(path: str, rgb8: np.ndarray) -> None:

@@ -949,6 +949,27 @@ int rm_renderer_stage_stats(rm_renderer* r, rm_stage_stats* out) {
 
 void rm_renderer_destroy(rm_renderer* r) { delete r; }
 
+/* Hand the cached device memory (stream-ordered pool of every visible device) and the cached pinned staging blocks back. */
+int rm_release_cached_memory(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); count = 0; }
+    int current = 0;
+    if (count) cudaGetDevice(&current);
+    for (int d = 0; d < count; d++) {
+        cudaMemPool_t pool;
+        if (cudaSetDevice(d) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess)
+            cudaMemPoolTrimTo(pool, 0);
+        cudaGetLastError();
+    }
+    if (count) cudaSetDevice(current);
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        for (PinnedBlock& f : g_pin_free) cudaFreeHost(f.p);
+        g_pin_free.clear();
+    }
+    return RM_OK;
+}
+
 #if defined(RM_TRAV_PROFILE)
 // tuning builds only: cycles per k_traverse phase {refill, walk, tests, finish, loop head, -, -, warps}; reading resets
 int rm_debug_trav_profile(unsigned long long* out8) {

@@ -127,3 +127,11 @@ def test_extreme_rays_bit_exact():
     got = product_scene(objs).intersect(rays)
     assert_hits_equal(got, want, "extreme rays")
     assert (want[0] >= 0).sum() > 10000
+
+
+def test_release_cached_memory_then_render_again():
+    objs, cam, spp = F.reflective_spheres(), F.camera(96, 64), 3
+    a, _ = gpu_render(objs, cam, spp, seed=2)
+    A.release_cached_memory()
+    b, _ = gpu_render(objs, cam, spp, seed=2)
+    assert np.array_equal(a, b)
