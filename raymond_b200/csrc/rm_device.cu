@@ -196,7 +196,12 @@ static int upload_grid(rm_device_scene* ds, const Grid& g, DevGrid* out) {
                  off_occ = off_cells + pad(nc * sizeof(uint2)), off_refs = off_occ + pad(n_occ * sizeof(unsigned)),
                  off_spht = off_refs + pad(nr * sizeof(unsigned)), host_total = off_spht + pad(nt * sizeof(float4)) + 256,
                  off_sph = host_total, total = off_sph + pad(nr * sizeof(float4)) + 256;
-    char* host = (char*)pinned_acquire(host_total);
+    // the flattened image of an immutable grid is built once and kept (pinned) with the grid; bigger ones are staged per upload
+    const bool keep_image = host_total <= kImageCacheLimit;
+    std::unique_lock<std::mutex> image_lock(g.image_mu, std::defer_lock);
+    if (keep_image) image_lock.lock();
+    const bool have_image = keep_image && g.image && g.image_bytes == host_total;
+    char* host = have_image ? (char*)g.image : (char*)pinned_acquire(host_total);
     if (!host) return fail(RM_ERR_OUT_OF_MEMORY, "cannot pin " + std::to_string(host_total) + " bytes of host staging memory");
     double* tri = (double*)(host + off_tri);
     double* shd = (double*)(host + off_shd);
@@ -249,18 +254,22 @@ static int upload_grid(rm_device_scene* ds, const Grid& g, DevGrid* out) {
             occ[w] = bits;
         }
     };
-    const unsigned hw = std::thread::hardware_concurrency();
-    const size_t workers = (nt + nc + nr < ((size_t)1 << 18)) ? 1 : std::min<size_t>(hw ? hw : 4, 8);
-    std::vector<std::thread> pool;
-    for (size_t w = 1; w < workers; w++)
-        pool.emplace_back([&, w] {
-            fill_triangles(nt * w / workers, nt * (w + 1) / workers);
-            fill_cells((nc * w / workers) & ~(size_t)31, w + 1 == workers ? nc : (nc * (w + 1) / workers) & ~(size_t)31);
-        });
-    fill_triangles(0, nt / workers);
-    fill_cells(0, workers == 1 ? nc : (nc / workers) & ~(size_t)31);
-    if (nr) memcpy(refs, g.references.data(), nr * sizeof(unsigned));
-    for (std::thread& t : pool) t.join();
+    if (!have_image) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        const size_t workers = (nt + nc + nr < ((size_t)1 << 18)) ? 1 : std::min<size_t>(hw ? hw : 4, 8);
+        std::vector<std::thread> pool;
+        for (size_t w = 1; w < workers; w++)
+            pool.emplace_back([&, w] {
+                fill_triangles(nt * w / workers, nt * (w + 1) / workers);
+                fill_cells((nc * w / workers) & ~(size_t)31, w + 1 == workers ? nc : (nc * (w + 1) / workers) & ~(size_t)31);
+            });
+        fill_triangles(0, nt / workers);
+        fill_cells(0, workers == 1 ? nc : (nc / workers) & ~(size_t)31);
+        if (nr) memcpy(refs, g.references.data(), nr * sizeof(unsigned));
+        for (std::thread& t : pool) t.join();
+        if (keep_image) { g.image = host; g.image_bytes = host_total; }
+    }
+    if (keep_image) image_lock.unlock();       // the image is read-only from here on
     void* dev = nullptr;
     cudaError_t e = dev_malloc(&dev, total);
     if (e == cudaSuccess) {
@@ -274,9 +283,9 @@ static int upload_grid(rm_device_scene* ds, const Grid& g, DevGrid* out) {
                 (const float4*)((char*)dev + off_spht), (const unsigned*)((char*)dev + off_refs), nr, (float4*)((char*)dev + off_sph));
             e = cudaGetLastError();
         }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(0);      // the staging block goes back to the pool on return
+        if (e == cudaSuccess) e = cudaStreamSynchronize(0);      // a staging block goes back to the pool on return
     }
-    pinned_release(host);
+    if (!keep_image) pinned_release(host);
     if (e != cudaSuccess) return fail(RM_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(e));
     d.tri = (const double*)((char*)dev + off_tri);
     d.shd = (const double*)((char*)dev + off_shd);

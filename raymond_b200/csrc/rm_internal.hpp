@@ -31,6 +31,11 @@ rm_aabb mesh_bounds(const rm_triangle* tris, size_t n);    // Mesh::find_mesh_bo
 // `mapping_table`) and `mapping_table` ([count, tri...] per cell, acc_grid.rs:67-74);
 // here the same per-cell lists, in the same ascending-triangle order, are stored
 // as cell_start[c]..cell_start[c+1] into `references`.
+// Page-locked host staging blocks, cached across calls (pinning is the expensive part of a short upload).
+// Defined in rm_device.cu.  acquire() returns nullptr when pinning fails.
+void* pinned_acquire(size_t bytes);
+void pinned_release(void* p);
+
 struct Grid {
     std::vector<rm_triangle> triangles;
     rm_aabb bounds;
@@ -39,7 +44,17 @@ struct Grid {
     std::vector<uint32_t> cell_start;   // n_cells + 1
     std::vector<uint32_t> references;   // triangle indices
     uint64_t n_cells() const { return resolution[0] * resolution[1] * resolution[2]; }
+    // The grid as the device wants it (upload_grid's host block), kept in pinned memory after the first upload so that
+    // every later upload of this immutable grid is one H2D copy with no flattening.  Only for images <= kImageCacheLimit.
+    mutable std::mutex image_mu;
+    mutable void* image = nullptr;
+    mutable size_t image_bytes = 0;
+    Grid() = default;
+    Grid(const Grid&) = delete;
+    Grid& operator=(const Grid&) = delete;
+    ~Grid() { pinned_release(image); }
 };
+constexpr size_t kImageCacheLimit = (size_t)2 << 30;
 // AccGrid::build_from_mesh                                 acc_grid.rs:36-83
 int grid_dims(const rm_aabb& bounds, size_t n, uint64_t res[3], double cell[3]);
 int build_grid(std::vector<rm_triangle>&& tris, const rm_aabb& bounds, std::shared_ptr<Grid>* out);
@@ -61,10 +76,6 @@ struct TileRect { size_t left, top, width, height; };
 // tile split of render_tiled                               src/trace.rs:142-173
 std::vector<TileRect> tile_layout(size_t W, size_t H, size_t tw, size_t th);
 
-// Page-locked host staging blocks, cached across calls (pinning is the expensive part of a short upload).
-// Defined in rm_device.cu.  acquire() returns nullptr when pinning fails.
-void* pinned_acquire(size_t bytes);
-void pinned_release(void* p);
 // Device memory from the cached stream-ordered pool (rm_device.cu); dev_alloc returns a cudaError_t value (0 = ok).
 // Sum of the accumulators of several renderers (one per device) into pinned host memory: peer copies onto the first
 // renderer's device + an add kernel per peer, in renderer order (rm_device.cu).  Synchronises every renderer's stream.

@@ -14,8 +14,14 @@ using namespace rm;
 // reference clones a Tile into every message (src/trace.rs:212-218); here the tiles of one checkpoint share one
 // frame snapshot and are sliced out of it when a message is delivered.
 struct FrameSnapshot {
-    std::vector<rm_vec3> sums;      // W * H, row-major
+    rm_vec3* sums = nullptr;        // W * H, row-major: the pinned block the D2H copy landed in (pageable when pinning fails
+    bool pinned = false;            // or too much is already held by undelivered checkpoints)
+    size_t bytes = 0;
     size_t W = 0;
+    FrameSnapshot() = default;
+    FrameSnapshot(const FrameSnapshot&) = delete;
+    FrameSnapshot& operator=(const FrameSnapshot&) = delete;
+    ~FrameSnapshot();
 };
 
 struct PendingMessage {
@@ -43,6 +49,30 @@ struct rm_task {
 
 namespace {
 
+std::atomic<size_t> g_snapshot_pinned_bytes{0};
+constexpr size_t kSnapshotPinnedLimit = (size_t)4 << 30;
+
+std::shared_ptr<FrameSnapshot> new_snapshot(size_t W, size_t H) {
+    auto f = std::make_shared<FrameSnapshot>();
+    f->W = W;
+    f->bytes = std::max<size_t>(W * H, 1) * sizeof(rm_vec3);
+    if (g_snapshot_pinned_bytes.load() + f->bytes <= kSnapshotPinnedLimit) f->sums = (rm_vec3*)pinned_acquire(f->bytes);
+    f->pinned = f->sums != nullptr;
+    if (f->pinned) g_snapshot_pinned_bytes += f->bytes;
+    else f->sums = (rm_vec3*)malloc(f->bytes);
+    if (!f->sums) throw std::bad_alloc();
+    return f;
+}
+
+}  // namespace
+
+FrameSnapshot::~FrameSnapshot() {
+    if (pinned) { pinned_release(sums); g_snapshot_pinned_bytes -= bytes; }
+    else free(sums);
+}
+
+namespace {
+
 // Tile { sample_count, width, height, left, top, data }: an independent copy the receiver owns
 bool make_tile(const PendingMessage& m, rm_tile* out) {
     const TileRect& r = m.rect;
@@ -51,17 +81,14 @@ bool make_tile(const PendingMessage& m, rm_tile* out) {
     out->data = (rm_vec3*)malloc(std::max<size_t>(r.width * r.height, 1) * sizeof(rm_vec3));
     if (!out->data) return false;
     for (size_t y = 0; y < r.height; y++)
-        memcpy(out->data + y * r.width, m.frame->sums.data() + (r.top + y) * m.frame->W + r.left, r.width * sizeof(rm_vec3));
+        memcpy(out->data + y * r.width, m.frame->sums + (r.top + y) * m.frame->W + r.left, r.width * sizeof(rm_vec3));
     return true;
 }
 
-void post_tiles(rm_task* t, uint32_t kind, size_t sample_count, const rm_vec3* sums) {
+void post_tiles(rm_task* t, uint32_t kind, size_t sample_count, const std::shared_ptr<FrameSnapshot>& frame) {
     const size_t W = t->settings.camera_settings.backbuffer_width, H = t->settings.camera_settings.backbuffer_height;
     std::vector<TileRect> tiles = tile_layout(W, H, t->settings.tile_size[0], t->settings.tile_size[1]);
     const int world = t->options.world_size > 1 ? t->options.world_size : 1;
-    auto frame = std::make_shared<FrameSnapshot>();
-    frame->W = W;
-    frame->sums.assign(sums, sums + W * H);
     std::deque<PendingMessage> batch;
     for (size_t i = 0; i < tiles.size(); i++) {
         if (t->options.partition == RM_PARTITION_TILES && (int)(i % (size_t)world) != t->options.rank) continue;
@@ -91,10 +118,9 @@ void drive(rm_task* t) {
     const size_t total = split_samples ? (s.sample_count > first ? (s.sample_count - first + world - 1) / world : 0) : s.sample_count;
     const bool split_local = G > 1 && t->options.partition == RM_PARTITION_SAMPLES;
     int st = RM_OK;
-    // the frame of running sums lands in a pinned block (cached across tasks): D2H at link speed
-    rm_vec3* sums = (rm_vec3*)pinned_acquire(std::max<size_t>(W * H, 1) * sizeof(rm_vec3));
+    // every checkpoint's frame of running sums lands in its own snapshot (a pinned block, cached across tasks: D2H at link
+    // speed, and the messages slice their tiles straight out of it)
     try {
-        if (!sums) throw std::bad_alloc();
         // TileProgressed every `samples_per_iteration` passes (src/trace.rs:217-219)
         const size_t chunk = s.samples_per_iteration ? s.samples_per_iteration : (total ? total : 1);
         size_t done = 0;
@@ -113,16 +139,19 @@ void drive(rm_task* t) {
             }
             done += n;
             if (st == RM_OK && done < total) {
-                st = reduce_accumulators_to_host(t->renderers.data(), (int)G, sums);
-                if (st == RM_OK) post_tiles(t, RM_TILE_PROGRESSED, done, sums);
+                std::shared_ptr<FrameSnapshot> frame = new_snapshot(W, H);
+                st = reduce_accumulators_to_host(t->renderers.data(), (int)G, frame->sums);
+                if (st == RM_OK) post_tiles(t, RM_TILE_PROGRESSED, done, frame);
             }
         }
-        if (st == RM_OK) st = reduce_accumulators_to_host(t->renderers.data(), (int)G, sums);
-        if (st == RM_OK) post_tiles(t, RM_TILE_FINISHED, total, sums);      // src/trace.rs:211-212
+        if (st == RM_OK) {
+            std::shared_ptr<FrameSnapshot> frame = new_snapshot(W, H);
+            st = reduce_accumulators_to_host(t->renderers.data(), (int)G, frame->sums);
+            if (st == RM_OK) post_tiles(t, RM_TILE_FINISHED, total, frame);      // src/trace.rs:211-212
+        }
     } catch (const std::bad_alloc&) {
         st = fail(RM_ERR_OUT_OF_MEMORY, "out of host memory in the render driver");
     }
-    pinned_release(sums);
     rm_stats stats{};
     for (size_t g = 0; g < G; g++) {
         rm_stats one{};
@@ -235,7 +264,7 @@ int rm_task_await(rm_task* t, rm_vec3* out) {
             const double c = (double)m.sample_count;
             const size_t a = std::max(y0, m.rect.top), b = std::min(y1, m.rect.top + m.rect.height);
             for (size_t y = a; y < b; y++) {
-                const rm_vec3* src = m.frame->sums.data() + y * m.frame->W + m.rect.left;
+                const rm_vec3* src = m.frame->sums + y * m.frame->W + m.rect.left;
                 rm_vec3* dst = out + y * W + m.rect.left;
                 for (size_t x = 0; x < m.rect.width; x++) dst[x] = rm_vec3{src[x].x / c, src[x].y / c, src[x].z / c};
             }
