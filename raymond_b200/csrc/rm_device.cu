@@ -882,23 +882,49 @@ int rm_renderer_sync(rm_renderer* r) {
     return RM_OK;
 }
 
-int rm_renderer_read_sums(rm_renderer* r, rm_vec3* out) {
-    if (!r || !out) return fail(RM_ERR_INVALID_ARGUMENT, "rm_renderer_read_sums: null argument");
+// The accumulator to (pageable) caller memory: D2H at link speed into a cached pinned block, then a few host threads move
+// it on, dividing by `divisor` on the way (tile.data[..] / tile.sample_count as f64, src/trace.rs:95) when it is not 0.
+static int read_accumulator(rm_renderer* r, rm_vec3* out, double divisor) {
     RM_CUDA(cudaSetDevice(r->device));
     const size_t n = r->settings.camera_settings.backbuffer_width * r->settings.camera_settings.backbuffer_height;
-    RM_CUDA(cudaMemcpyAsync(out, r->accum, n * sizeof(rm_vec3), cudaMemcpyDeviceToHost, r->stream));
-    RM_CUDA(cudaStreamSynchronize(r->stream));
+    rm_vec3* pin = (rm_vec3*)pinned_acquire(std::max<size_t>(n, 1) * sizeof(rm_vec3));
+    cudaError_t e = cudaMemcpyAsync(pin ? pin : out, r->accum, n * sizeof(rm_vec3), cudaMemcpyDeviceToHost, r->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(r->stream);
+    if (e != cudaSuccess) {
+        pinned_release(pin);
+        return fail(RM_ERR_CUDA, std::string("D2H of the accumulator: ") + cudaGetErrorString(e));
+    }
     harvest_events(r);
+    const rm_vec3* src = pin ? pin : out;
+    auto rows = [&](size_t lo, size_t hi) {
+        if (divisor != 0.0) for (size_t i = lo; i < hi; i++) out[i] = rm_vec3{src[i].x / divisor, src[i].y / divisor, src[i].z / divisor};
+        else if (src != out) memcpy((void*)(out + lo), (const void*)(src + lo), (hi - lo) * sizeof(rm_vec3));
+    };
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t workers = n < ((size_t)1 << 18) ? 1 : std::min<size_t>(hw ? hw : 4, 8);
+    std::vector<std::thread> pool;
+    for (size_t w = 1; w < workers; w++) pool.emplace_back(rows, n * w / workers, n * (w + 1) / workers);
+    rows(0, n / workers);
+    for (std::thread& t : pool) t.join();
+    pinned_release(pin);
     return RM_OK;
 }
 
+int rm_renderer_read_sums(rm_renderer* r, rm_vec3* out) {
+    if (!r || !out) return fail(RM_ERR_INVALID_ARGUMENT, "rm_renderer_read_sums: null argument");
+    return read_accumulator(r, out, 0.0);
+}
+
 int rm_renderer_read_frame(rm_renderer* r, size_t sample_count, rm_vec3* out) {
-    if (int st = rm_renderer_read_sums(r, out)) return st;
-    // tile.data[..] / tile.sample_count as f64             src/trace.rs:95
-    const size_t n = r->settings.camera_settings.backbuffer_width * r->settings.camera_settings.backbuffer_height;
-    const double c = (double)sample_count;
-    for (size_t i = 0; i < n; i++) { out[i].x /= c; out[i].y /= c; out[i].z /= c; }
-    return RM_OK;
+    if (!r || !out) return fail(RM_ERR_INVALID_ARGUMENT, "rm_renderer_read_frame: null argument");
+    // a zero sample_count divides by zero like the reference would (inf / NaN), it does not mean "no division"
+    if (sample_count == 0) {
+        if (int st = read_accumulator(r, out, 0.0)) return st;
+        const size_t n = r->settings.camera_settings.backbuffer_width * r->settings.camera_settings.backbuffer_height;
+        for (size_t i = 0; i < n; i++) { out[i].x /= 0.0; out[i].y /= 0.0; out[i].z /= 0.0; }
+        return RM_OK;
+    }
+    return read_accumulator(r, out, (double)sample_count);
 }
 
 int rm_renderer_read_rgb8(rm_renderer* r, size_t sample_count, double exposure, double gamma, uint8_t* out) {
