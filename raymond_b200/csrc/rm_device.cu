@@ -68,6 +68,8 @@ std::vector<PinnedBlock> g_pin_free, g_pin_busy;
 constexpr size_t kPinnedCacheLimit = (size_t)8 << 30;      // blocks beyond 8 GiB of cache are unpinned on release
 }  // namespace
 
+std::atomic<size_t> Grid::g_grid_image_bytes{0};
+
 void* pinned_acquire(size_t bytes) {
     bytes = std::max<size_t>(bytes, 4096);
     std::lock_guard<std::mutex> lk(g_pin_mu);
@@ -197,10 +199,10 @@ static int upload_grid(rm_device_scene* ds, const Grid& g, DevGrid* out) {
                  off_spht = off_refs + pad(nr * sizeof(unsigned)), host_total = off_spht + pad(nt * sizeof(float4)) + 256,
                  off_sph = host_total, total = off_sph + pad(nr * sizeof(float4)) + 256;
     // the flattened image of an immutable grid is built once and kept (pinned) with the grid; bigger ones are staged per upload
-    const bool keep_image = host_total <= kImageCacheLimit;
-    std::unique_lock<std::mutex> image_lock(g.image_mu, std::defer_lock);
-    if (keep_image) image_lock.lock();
-    const bool have_image = keep_image && g.image && g.image_bytes == host_total;
+    std::unique_lock<std::mutex> image_lock(g.image_mu);
+    const bool have_image = g.image && g.image_bytes == host_total;
+    const bool keep_image = have_image || (host_total <= kImageCacheLimit && Grid::g_grid_image_bytes.load() + host_total <= kImageCacheTotalLimit);
+    if (!keep_image) image_lock.unlock();
     char* host = have_image ? (char*)g.image : (char*)pinned_acquire(host_total);
     if (!host) return fail(RM_ERR_OUT_OF_MEMORY, "cannot pin " + std::to_string(host_total) + " bytes of host staging memory");
     double* tri = (double*)(host + off_tri);
@@ -267,7 +269,7 @@ static int upload_grid(rm_device_scene* ds, const Grid& g, DevGrid* out) {
         fill_cells(0, workers == 1 ? nc : (nc / workers) & ~(size_t)31);
         if (nr) memcpy(refs, g.references.data(), nr * sizeof(unsigned));
         for (std::thread& t : pool) t.join();
-        if (keep_image) { g.image = host; g.image_bytes = host_total; }
+        if (keep_image) { g.image = host; g.image_bytes = host_total; Grid::g_grid_image_bytes += host_total; }
     }
     if (keep_image) image_lock.unlock();       // the image is read-only from here on
     void* dev = nullptr;

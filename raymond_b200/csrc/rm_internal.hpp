@@ -52,9 +52,11 @@ struct Grid {
     Grid() = default;
     Grid(const Grid&) = delete;
     Grid& operator=(const Grid&) = delete;
-    ~Grid() { pinned_release(image); }
+    ~Grid() { if (image) { pinned_release(image); g_grid_image_bytes -= image_bytes; } }
+    static std::atomic<size_t> g_grid_image_bytes;      // pinned bytes held by all grids' images (rm_device.cu)
 };
-constexpr size_t kImageCacheLimit = (size_t)2 << 30;
+constexpr size_t kImageCacheLimit = (size_t)2 << 30;          // largest image kept with its grid
+constexpr size_t kImageCacheTotalLimit = (size_t)8 << 30;     // ... and how much all grids together may keep pinned
 // AccGrid::build_from_mesh                                 acc_grid.rs:36-83
 int grid_dims(const rm_aabb& bounds, size_t n, uint64_t res[3], double cell[3]);
 int build_grid(std::vector<rm_triangle>&& tris, const rm_aabb& bounds, std::shared_ptr<Grid>* out);
