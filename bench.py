@@ -292,7 +292,7 @@ def bench_ours(args):
         counted.close()
         total_ms = sum(sum(v) for v in d_ms.values())
         stages, per_kernel = [], {}
-        kernel_bytes, survive = {}, {}
+        kernel_bytes, survive, kernel_flops, ref_flops_min = {}, {}, {}, {}
         for d in range(0, A.STAGE_SLOTS):
             for k in kinds:
                 if d_launch[k][d] == 0:
@@ -314,6 +314,12 @@ def bench_ours(args):
                     # per occupied cell, a 16-B bounding sphere per candidate, reference + positions (100 B) per candidate not proven a miss
                     kernel_bytes[d] = (144.0 + 4.0 * C_ + 8.0 * cs["occupied_cells"][d] / g_ + 16.0 * T_ + 100.0 * cs["evaluated_tests"][d] / g_) * d_grid[d]
                     survive[d] = cs["evaluated_tests"][d] / max(cs["triangle_tests"][d], 1)
+                    # f64 add/sub/mul/div this kernel executes per grid ray: 1 per cell step (t_max += t_delta), 19 per bounding-sphere
+                    # pre-test, and the counted exits (20 / 30 / 46 / 52) of the Triangle::intersects calls it evaluates; the reference
+                    # runs Triangle::intersects on all T candidates (>= 20 each for the ones proven misses here)
+                    fl_eval = cs["evaluated_test_flops"][d] / g_
+                    kernel_flops[d] = (C_ + 19.0 * T_ + fl_eval) * d_grid[d]
+                    ref_flops_min[d] = (C_ + 20.0 * (T_ - cs["evaluated_tests"][d] / g_) + fl_eval) * d_grid[d]
                 else:
                     # shade: ray + throughput + id + hit in (92 B), next ray out (76 B) or radiance out (24 B); +144 B (positions, normals) per shaded triangle
                     units = d_rays[d]
@@ -336,7 +342,17 @@ def bench_ours(args):
         top = max(per_kernel, key=lambda k: per_kernel[k]["ms"])
         pk = per_kernel[top]
         ach = pk["bytes"] / (pk["ms"] * 1e-3) / 1e9 if pk["ms"] > 0 else 0.0
-        roofline = {"bound": "hbm", "kernel": "k_" + top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+        fp64 = None
+        if top == "traverse":
+            fp64_peak = A.measure_fp64_rate(local)
+            ach_ops = sum(kernel_flops.values()) / (pk["ms"] * 1e-3) / 1e9
+            fp64 = {"peak_gops": fp64_peak, "peak_source": "measured live: independent DADD/DMUL stream, no FMA (the library is compiled -fmad=false "
+                                                           "to replay the reference's unfused f64 arithmetic), rm_measure_fp64_rate",
+                    "kernel_ops_per_unit": sum(kernel_flops.values()) / max(pk["units"], 1), "achieved_gops": ach_ops, "frac": ach_ops / fp64_peak,
+                    "reference_algorithm_ops_per_unit_min": sum(ref_flops_min.values()) / max(pk["units"], 1),
+                    "what": "f64 add/sub/mul/div per grid ray executed by k_traverse (C + 19 T + counted Triangle::intersects exits), against "
+                            "the device's no-FMA f64 rate; compares, selects, integer and address work are not counted"}
+        roofline = {"bound": "hbm", "kernel": "k_" + top, "fp64": fp64, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": (NCU_TRAFFIC_PER_UNIT["k_" + top] * pk["units"] / max(pk["launches"], 1)) if "k_" + top in NCU_TRAFFIC_PER_UNIT else None, "peak_source": peak_src,
                     "alg_bytes_per_launch": pk["bytes"] / max(pk["launches"], 1), "alg_bytes_per_unit": pk["bytes"] / max(pk["units"], 1),
                     "unit_name": "grid ray" if top == "traverse" else ("path" if top == "accumulate" else "ray"),

@@ -338,6 +338,8 @@ typedef struct rm_stage_stats {
     uint64_t shaded_triangles[RM_STAGE_SLOTS];
     uint64_t evaluated_tests[RM_STAGE_SLOTS];  /* of triangle_tests, the ones NOT proven misses by the bounding-sphere pre-test (RM_FLAG_COUNT_WORK) */
     uint64_t occupied_cells[RM_STAGE_SLOTS];   /* of cells, the ones with a non-empty list (RM_FLAG_COUNT_WORK) */
+    uint64_t evaluated_test_flops[RM_STAGE_SLOTS]; /* f64 add/sub/mul/div executed by the evaluated Triangle::intersects calls: 20, 30, 46 or 52
+                                                * per call depending on the exit taken, triangle.rs:11-44 (RM_FLAG_COUNT_WORK) */
 } rm_stage_stats;
 int rm_renderer_stage_stats(rm_renderer* r, rm_stage_stats* out);
 void rm_renderer_destroy(rm_renderer* r);
@@ -346,6 +348,10 @@ void rm_renderer_destroy(rm_renderer* r);
 int rm_tonemap_rgb8(const rm_vec3* frame_host, size_t pixels, double exposure, double gamma, int device, uint8_t* out_host);
 /* image.save("output.png")                      cli_old/src/main.rs:194-197: 8-bit RGB PNG (host code). */
 int rm_write_png(const char* path, const uint8_t* rgb8, size_t width, size_t height);
+
+/* Diagnostic for the roofline: the f64 operation rate this device sustains on a stream of independent DADD / DMUL
+ * (no FMA, as this library is compiled), in Gop/s.  Runs a ~10 ms kernel on `device`. */
+int rm_measure_fp64_rate(int device, double* gops_out);
 
 /* The library keeps the device memory of finished renders (a stream-ordered pool per GPU) and its pinned staging blocks
  * for the next call; this returns them to the driver.  Safe to call at any time no render is in flight. */

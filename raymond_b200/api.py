@@ -107,12 +107,12 @@ KERNEL_KINDS = ("setup", "traverse", "shade", "accumulate")
 
 class StageStatsC(C.Structure):
     _fields_ = [("ms", (C.c_double * STAGE_SLOTS) * 4), ("launches", (C.c_uint64 * STAGE_SLOTS) * 4)] + \
-               [(n, C.c_uint64 * STAGE_SLOTS) for n in ("rays", "grid_rays", "cells", "triangle_tests", "shaded_triangles", "evaluated_tests", "occupied_cells")]
+               [(n, C.c_uint64 * STAGE_SLOTS) for n in ("rays", "grid_rays", "cells", "triangle_tests", "shaded_triangles", "evaluated_tests", "occupied_cells", "evaluated_test_flops")]
 
     def as_dict(self) -> dict:
         d = {"ms": {k: list(self.ms[i]) for i, k in enumerate(KERNEL_KINDS)},
              "launches": {k: list(self.launches[i]) for i, k in enumerate(KERNEL_KINDS)}}
-        for n in ("rays", "grid_rays", "cells", "triangle_tests", "shaded_triangles", "evaluated_tests", "occupied_cells"):
+        for n in ("rays", "grid_rays", "cells", "triangle_tests", "shaded_triangles", "evaluated_tests", "occupied_cells", "evaluated_test_flops"):
             d[n] = list(getattr(self, n))
         return d
 
@@ -130,7 +130,7 @@ ABI_SYMBOLS = [
     "rm_device_scene_intersect", "rm_primary_rays_device", "rm_renderer_create", "rm_renderer_create_on", "rm_renderer_render",
     "rm_renderer_accum_device", "rm_renderer_clear", "rm_renderer_sync", "rm_renderer_read_sums", "rm_renderer_read_frame",
     "rm_renderer_stats", "rm_renderer_stage_stats", "rm_renderer_destroy", "rm_tile_layout", "rm_renderer_read_rgb8", "rm_tonemap_rgb8",
-    "rm_write_png", "rm_project_load_scene", "rm_message_to_json", "rm_release_cached_memory",
+    "rm_write_png", "rm_project_load_scene", "rm_message_to_json", "rm_release_cached_memory", "rm_measure_fp64_rate",
 ]
 
 _lib = None
@@ -197,6 +197,7 @@ def lib():
         "rm_project_load_scene": (vp, [C.c_char_p, P(i32)]),
         "rm_message_to_json": (sz, [P(MessageC), C.c_char_p, sz]),
         "rm_release_cached_memory": (i32, []),
+        "rm_measure_fp64_rate": (i32, [i32, C.POINTER(C.c_double)]),
         "rm_renderer_stats": (i32, [vp, P(StatsC)]),
         "rm_renderer_stage_stats": (i32, [vp, P(StageStatsC)]),
         "rm_renderer_destroy": (None, [vp]),
@@ -610,6 +611,13 @@ def tonemap(frame: np.ndarray, exposure: float = 1.0, gamma: float = 2.2, device
 def release_cached_memory() -> None:
     """Return the cached device pool and pinned staging blocks to the driver."""
     _check(lib().rm_release_cached_memory())
+
+
+def measure_fp64_rate(device: int = 0) -> float:
+    """Sustained f64 operation rate (independent DADD / DMUL, no FMA) of `device` in Gop/s: the roofline's compute ceiling."""
+    g = C.c_double(0.0)
+    _check(lib().rm_measure_fp64_rate(device, C.byref(g)))
+    return g.value
 
 
 def write_png(path: str, rgb8: np.ndarray) -> None:

@@ -980,11 +980,53 @@ int rm_renderer_stage_stats(rm_renderer* r, rm_stage_stats* out) {
         out->shaded_triangles[i] = t.shaded[i];
         out->evaluated_tests[i] = t.survivors[i];
         out->occupied_cells[i] = t.occupied[i];
+        out->evaluated_test_flops[i] = t.test_flops[i];
     }
     return RM_OK;
 }
 
 void rm_renderer_destroy(rm_renderer* r) { delete r; }
+
+// 8 independent chains per thread of alternating DMUL / DADD (this file is compiled with -fmad=false: they stay two instructions)
+__global__ void __launch_bounds__(256) k_fp64_rate(double* out, int iters, double m, double c) {
+    double a[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) a[j] = 1.0 + 1e-3 * (double)(threadIdx.x + j);
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) { a[j] = a[j] * m; a[j] = a[j] + c; }
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) sum += a[j];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = sum;
+}
+
+int rm_measure_fp64_rate(int device, double* gops_out) {
+    if (!gops_out) return fail(RM_ERR_INVALID_ARGUMENT, "rm_measure_fp64_rate: null argument");
+    RM_CUDA(cudaSetDevice(device));
+    const int sms = sm_count(device), blocks = sms * 8, iters = 4096;
+    double* out = nullptr;
+    RM_CUDA(dev_malloc(&out, (size_t)blocks * 256 * sizeof(double)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 0.f;
+    cudaError_t e = cudaSuccess;
+    for (int rep = 0; rep < 4 && e == cudaSuccess; rep++) {          // rep 0 warms up
+        cudaEventRecord(e0, 0);
+        k_fp64_rate<<<blocks, 256>>>(out, iters, 0.9999999, 1e-7);
+        cudaEventRecord(e1, 0);
+        e = cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && (best == 0.f || ms < best)) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    dev_free(out);
+    if (e != cudaSuccess || best <= 0.f) return fail(RM_ERR_CUDA, std::string("fp64 rate kernel: ") + cudaGetErrorString(e));
+    *gops_out = (double)blocks * 256.0 * (double)iters * 16.0 / ((double)best * 1e-3) / 1e9;
+    return RM_OK;
+}
 
 /* Hand the cached device memory (stream-ordered pool of every visible device) and the cached pinned staging blocks back. */
 int rm_release_cached_memory(void) {

@@ -109,7 +109,7 @@ constexpr int kTravDoubles = 16;
 
 struct DevTotals {
     unsigned long long samples, rays, nonfinite;
-    unsigned long long stage_rays[RM_STAGE_SLOTS], grid_rays[RM_STAGE_SLOTS], cells[RM_STAGE_SLOTS], tests[RM_STAGE_SLOTS], shaded[RM_STAGE_SLOTS], survivors[RM_STAGE_SLOTS], occupied[RM_STAGE_SLOTS];
+    unsigned long long stage_rays[RM_STAGE_SLOTS], grid_rays[RM_STAGE_SLOTS], cells[RM_STAGE_SLOTS], tests[RM_STAGE_SLOTS], shaded[RM_STAGE_SLOTS], survivors[RM_STAGE_SLOTS], occupied[RM_STAGE_SLOTS], test_flops[RM_STAGE_SLOTS];
 };
 
 // Per-batch device counters, all indexed by depth (zeroed once per batch).
@@ -326,20 +326,25 @@ __device__ __forceinline__ TriPos load_triangle(const double* __restrict__ tp) {
     ld256_nc(tp + 8, p.v2z, p0, p1, p2);
     return p;
 }
-__device__ __forceinline__ bool hit_triangle(const TriPos& p, D3 o, D3 d, double& t_out) {
+// `flops` (instrumented builds): the add / sub / mul / div count of the exit taken — 20, 30, 46 or 52
+__device__ __forceinline__ bool hit_triangle(const TriPos& p, D3 o, D3 d, double& t_out, unsigned* flops = nullptr) {
     const D3 e1 = d3(p.v1x - p.v0x, p.v1y - p.v0y, p.v1z - p.v0z);
     const D3 e2 = d3(p.v2x - p.v0x, p.v2y - p.v0y, p.v2z - p.v0z);
     const D3 h = cross(d, e2);
     const double a = dot(e1, h);
+    if (flops) *flops = 20u;
     if (a < 0.00000001 && a > -0.00000001) return false;
     const double f = 1.0 / a;
     const D3 s = d3(o.x - p.v0x, o.y - p.v0y, o.z - p.v0z);
     const double u = f * dot(s, h);
+    if (flops) *flops = 30u;
     if (u < 0.0 || u > 1.0) return false;
     const D3 q = cross(s, e1);
     const double v = f * dot(d, q);
+    if (flops) *flops = 46u;
     if (v < 0.0 || u + v > 1.0) return false;
     const double t = f * dot(e2, q);
+    if (flops) *flops = 52u;
     if (!(t > 0.00000001)) return false;
     t_out = t;
     return true;
@@ -722,7 +727,7 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
     int cx = 0, cy = 0, cz = 0, sx = 1, sy = 1, sz = 1;
     const unsigned rx = (unsigned)g.res[0], ry = (unsigned)g.res[1], rz = (unsigned)g.res[2];
     unsigned ray = 0, k = 0, cnt = 0;
-    unsigned n_cells = 0, n_tests = 0, n_surv = 0, n_occ = 0;
+    unsigned n_cells = 0, n_tests = 0, n_surv = 0, n_occ = 0, n_flops = 0;
 #if defined(RM_TRAV_PROFILE)
     unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long prof_t = clock64();
@@ -910,7 +915,10 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
                 const TriPos tp = load_triangle(g.tri + (size_t)__ldg(&g.refs[c_pos]) * 12);
                 const double2 r0 = sh.ray[c_owner][0], r1 = sh.ray[c_owner][1], r2 = sh.ray[c_owner][2];
                 double t;
-                if (hit_triangle(tp, d3(r0.x, r0.y, r1.x), d3(r1.y, r2.x, r2.y), t)) {
+                unsigned fl = 0;
+                const bool is_hit = hit_triangle(tp, d3(r0.x, r0.y, r1.x), d3(r1.y, r2.x, r2.y), t, COUNT ? &fl : nullptr);
+                if (COUNT) n_flops += fl;
+                if (is_hit) {
                     tb = (unsigned long long)__double_as_longlong(t);      // t > 1e-8: bit order = numeric order
                     got = true;
                     atomicMin(&sh.cand_t[c_owner], tb);
@@ -955,12 +963,13 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
 #endif
     if (COUNT) {
         const unsigned c = __reduce_add_sync(FULL, n_cells), t = __reduce_add_sync(FULL, n_tests);
-        const unsigned sv = __reduce_add_sync(FULL, n_surv), oc = __reduce_add_sync(FULL, n_occ);
+        const unsigned sv = __reduce_add_sync(FULL, n_surv), oc = __reduce_add_sync(FULL, n_occ), fl = __reduce_add_sync(FULL, n_flops);
         if (lane == 0) {
             atomicAdd(&a.totals->cells[stage_slot(a.depth)], (unsigned long long)c);
             atomicAdd(&a.totals->tests[stage_slot(a.depth)], (unsigned long long)t);
             atomicAdd(&a.totals->survivors[stage_slot(a.depth)], (unsigned long long)sv);
             atomicAdd(&a.totals->occupied[stage_slot(a.depth)], (unsigned long long)oc);
+            atomicAdd(&a.totals->test_flops[stage_slot(a.depth)], (unsigned long long)fl);
         }
     }
 }
