@@ -901,6 +901,7 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
                 if (COUNT && pass) n_surv++;
                 base += 32u;
                 __syncwarp();
+                RM_PROF_MARK(5);
                 continue;
             }
             if (q_count == 0u) break;
@@ -937,6 +938,7 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
                 sh.cand_pos[lane] = ~0u;
             }
             __syncwarp();       // the ring slots just read may be rewritten by the next stage-1 round
+            RM_PROF_MARK(6);
         }
         RM_PROF_MARK(2);
         // ---- C
@@ -957,7 +959,7 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
     }
 #if defined(RM_TRAV_PROFILE)
     if (lane == 0) {
-        for (int i = 0; i < 5; i++) atomicAdd(&g_trav_prof[i], prof[i]);
+        for (int i = 0; i < 7; i++) atomicAdd(&g_trav_prof[i], prof[i]);
         atomicAdd(&g_trav_prof[7], 1ull);
     }
 #endif

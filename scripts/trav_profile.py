@@ -15,6 +15,6 @@ r.render(0, spp); r.sync()
 L.rm_debug_trav_profile(out)
 ms = r.stats()["device_ms"] - s0
 v = list(out)
-tot = sum(v[:5])
-names = ["refill", "walk(A)", "tests(B)", "finish(C)", "loop head/scan"]
-print(f"frame {ms:7.2f} ms | " + "  ".join(f"{n} {100*x/tot:5.1f}%" for n, x in zip(names, v[:5])) + f" | warps {v[7]}  cycles/warp {tot/max(v[7],1)/1e6:.2f}M")
+tot = sum(v[:7])
+names = ["refill", "walk(A)", "pool set-up(B)", "finish(C)", "loop head", "stage-1 rounds(B)", "stage-2 rounds(B)"]
+print(f"frame {ms:7.2f} ms | " + "  ".join(f"{n} {100*x/tot:5.1f}%" for n, x in zip(names, v[:7])) + f" | warps {v[7]}  cycles/warp {tot/max(v[7],1)/1e6:.2f}M")
