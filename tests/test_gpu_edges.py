@@ -135,3 +135,44 @@ def test_release_cached_memory_then_render_again():
     A.release_cached_memory()
     b, _ = gpu_render(objs, cam, spp, seed=2)
     assert np.array_equal(a, b)
+
+
+def test_grid_image_is_reused_across_uploads_and_scenes():
+    """The flattened device image of an (immutable) grid is built at its first upload and kept pinned with the grid: later
+    uploads — the same scene again, another scene holding the same Arc<AccGrid>, an upload after the caches were dropped — must
+    give the same bits, for queries and for frames."""
+    tris = F.translate(F.dragon_standin(96, 24), (0.0, -0.2, 3.2))
+    grid = A.AccGrid.build_from_mesh(A.Mesh.new(tris))
+    s1 = A.Scene()
+    s1.push_grid(grid, A.Material.Metal((1, 0.8, 0.3), 0.2))
+    for ob in F.BOX_PLANES:
+        s1.push_plane(ob[1], ob[2], A.Material.from_fixture(ob[3]))
+    cam = F.camera(160, 96)
+    rays = O.primary_rays(cam)
+    first = s1.intersect(rays)
+    again = s1.intersect(rays)
+    A.release_cached_memory()
+    after_release = s1.intersect(rays)
+    s2 = A.Scene()
+    s2.push_sphere((0.0, 0.0, 30.0), 0.5, A.Material.Diffuse((1, 1, 1), 0.5))      # object indices shift by one
+    s2.push_grid(grid, A.Material.Diffuse((0.2, 0.9, 0.2), 0.5))
+    other = s2.intersect(rays)
+    grid_hits = first[0] == 0
+    assert grid_hits.sum() > 1000
+    for got, what in ((again, "second upload"), (after_release, "upload after release")):
+        assert_hits_equal(got, first, what)
+    assert np.array_equal(other[0][grid_hits], np.ones(grid_hits.sum(), dtype=other[0].dtype))
+    assert np.array_equal(other[1][grid_hits], first[1][grid_hits]) and np.array_equal(other[2][grid_hits].view(np.uint64), first[2][grid_hits].view(np.uint64))
+    st = A.Settings(A.CameraSettings.from_fixture(cam), 3)
+    frames = [A.render_tiled(s1, st, A.GpuOptions(seed=5)).await_() for _ in range(2)]
+    assert np.array_equal(frames[0], frames[1])
+
+
+def test_read_frame_is_sums_over_count():
+    objs, cam, spp = F.reflective_spheres(), F.camera(640, 480), 3        # above the threaded read-back threshold
+    sc = product_scene(objs)
+    r = A.Renderer(sc, A.Settings(A.CameraSettings.from_fixture(cam), spp), A.GpuOptions(seed=4))
+    r.render(0, spp)
+    sums, frame = r.read_sums(), r.read_frame(spp)
+    r.close()
+    assert np.array_equal(frame, sums / float(spp))
