@@ -189,6 +189,8 @@ def test_compute_without_a_device_is_an_error_not_a_fallback():
         A.Renderer(sc, settings(F.camera(8, 8), 1))
     with pytest.raises(A.RaymondError):
         A.DeviceScene(sc, 0)
+    with pytest.raises(A.RaymondError):
+        A.measure_fp64_rate(0)
 
 
 def test_product_does_not_import_the_oracle():
