@@ -59,6 +59,7 @@ extern "C" {
     pub fn rm_project_load_scene(path: *const c_char, status: *mut c_int) -> *mut rm_scene;                // Project::load + build_scene  project.rs:33-57
     pub fn rm_message_to_json(m: *const rm_message, buf: *mut c_char, cap: usize) -> usize;                // protocol.rs:9-14
     pub fn rm_tonemap_rgb8(frame: *const rm_vec3, pixels: usize, exposure: f64, gamma: f64, device: c_int, out: *mut u8) -> c_int; // cli_old main.rs:157-181
-    pub fn rm_write_png(path: *const c_char, rgb8: *const u8, width: usize, height: usize) -> c_int;
-    pub fn rm_release_cached_memory() -> c_int;      // cli_old main.rs:194-197
+    pub fn rm_write_png(path: *const c_char, rgb8: *const u8, width: usize, height: usize) -> c_int;       // cli_old main.rs:194-197
+    pub fn rm_release_cached_memory() -> c_int;
+    pub fn rm_measure_fp64_rate(device: c_int, gops_out: *mut f64) -> c_int;                                // diagnostic (roofline)
 }
