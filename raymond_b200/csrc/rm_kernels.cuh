@@ -580,6 +580,8 @@ __global__ void __launch_bounds__(kBlock, RM_SETUP_BLOCKS_PER_SM) k_setup(const 
         bool push = false;
         D3 o, d;
         Dda s;
+        double best_t = 0.0;        // closest hit among the objects already evaluated: travels with the traversal record
+        int best_obj = -1;
         if (i < n) {
             if (SRC == SRC_CAMERA) {
                 const unsigned q = i % rp.n_pixels, s_local = i / rp.n_pixels;
@@ -594,8 +596,6 @@ __global__ void __launch_bounds__(kBlock, RM_SETUP_BLOCKS_PER_SM) k_setup(const 
                 o = d3(r[0], r[1], r[2]);
                 d = d3(r[3], r[4], r[5]);
             }
-            double best_t = 0.0;
-            int best_obj = -1;
             if (a.analytic) {
                 // Scene::intersect over the Sphere / Plane objects, in order, strict <   scene.rs:54-68
                 double closest = DBL_MAX;
@@ -637,7 +637,7 @@ __global__ void __launch_bounds__(kBlock, RM_SETUP_BLOCKS_PER_SM) k_setup(const 
                 st256(rec, o.x, o.y, o.z, d.x);
                 st256(rec + 4, d.y, d.z, s.tmx, s.tmy);
                 st256(rec + 8, s.tmz, s.tdx, s.tdy, s.tdz);
-                st256(rec + 12, __hiloint2double(s.cy, s.cx), __hiloint2double((int)s.step, s.cz), __hiloint2double(0, (int)i), 0.0);
+                st256(rec + 12, __hiloint2double(s.cy, s.cx), __hiloint2double((int)s.step, s.cz), __hiloint2double(best_obj, (int)i), best_t);
             }
         }
     }
@@ -691,12 +691,14 @@ constexpr unsigned kRefillMin = RM_TRAV_REFILL_MIN;       // idle lanes that tri
 struct TravWarpShared {
     double2 ray[32][3];                // {o.x o.y} {o.z d.x} {d.y d.z} of the lane's ray (three 128-bit accesses)
     unsigned long long cand_t[32];     // this round's smallest distance bits per ray
-    unsigned cand_pos[32];             // ... and the earliest list position that has it
+    unsigned cand_tri[32];             // ... and the smallest triangle index that has it (= the earliest list position: a cell's list ascends)
     unsigned olane[32];                // q-th lane that contributes a list to the pool
     unsigned odelta[32];               // ... and (first reference of its cell) - (its first item): position = item + odelta
     double2 dd_lim[32];                // |d|^2 of the lane's ray, and the guard of cull_sphere
     unsigned s_pos[64];                // ring of candidates that survived the sphere pre-test: list position
     unsigned char s_owner[64];         // ... and the lane that owns the ray
+    double best_t[32];                 // the lane's ray: closest hit among the objects evaluated before this grid (from the
+    int best_obj[32];                  // traversal record), merged with the grid's answer when the ray finishes
 };
 
 enum TravState : unsigned { TS_IDLE = 0, TS_LOOK = 1, TS_STEP = 2, TS_READY = 3 };
@@ -755,6 +757,8 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
                     const unsigned neg = (unsigned)__double2hiint(q1);
                     sx = (neg & 1u) ? -1 : 1; sy = (neg & 2u) ? -1 : 1; sz = (neg & 4u) ? -1 : 1;
                     ray = (unsigned)__double2loint(q2);
+                    sh.best_obj[lane] = __double2hiint(q2);
+                    sh.best_t[lane] = q3;
                     sh.ray[lane][0] = make_double2(ox, oy);
                     sh.ray[lane][1] = make_double2(oz, dx);
                     sh.ray[lane][2] = make_double2(dy, dz);
@@ -852,9 +856,9 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
             }
         }
         sh.cand_t[lane] = ~0ull;
-        sh.cand_pos[lane] = ~0u;
+        sh.cand_tri[lane] = ~0u;
         unsigned long long best_t = kClosest0;       // per-cell closest of MY ray
-        unsigned best_pos = ~0u;
+        unsigned best_tri = ~0u;
         __syncwarp();
         // (owner lane, list position) of item rbase + lane; rbase is warp-uniform and every lane takes part
         auto locate = [&](unsigned rbase, unsigned& owner, unsigned& pos) {
@@ -909,11 +913,12 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
             const bool valid = lane < take;
             bool got = false;
             unsigned long long tb = 0;
-            unsigned c_owner = 0, c_pos = 0;
+            unsigned c_owner = 0, c_tri = 0;
             if (valid) {
                 const unsigned slot = (q_head + lane) & 63u;
-                c_owner = sh.s_owner[slot]; c_pos = sh.s_pos[slot];
-                const TriPos tp = load_triangle(g.tri + (size_t)__ldg(&g.refs[c_pos]) * 12);
+                c_owner = sh.s_owner[slot];
+                c_tri = __ldg(&g.refs[sh.s_pos[slot]]);
+                const TriPos tp = load_triangle(g.tri + (size_t)c_tri * 12);
                 const double2 r0 = sh.ray[c_owner][0], r1 = sh.ray[c_owner][1], r2 = sh.ray[c_owner][2];
                 double t;
                 unsigned fl = 0;
@@ -929,13 +934,13 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
             q_count -= take;
             if (__any_sync(FULL, got)) {
                 __syncwarp();
-                if (got && sh.cand_t[c_owner] == tb) atomicMin(&sh.cand_pos[c_owner], c_pos);
+                if (got && sh.cand_t[c_owner] == tb) atomicMin(&sh.cand_tri[c_owner], c_tri);
                 __syncwarp();
                 // strict < against the earlier rounds (they hold earlier list positions) and against 5712515.0
                 const unsigned long long ct = sh.cand_t[lane];
-                if (ct < best_t) { best_t = ct; best_pos = sh.cand_pos[lane]; }
+                if (ct < best_t) { best_t = ct; best_tri = sh.cand_tri[lane]; }
                 sh.cand_t[lane] = ~0ull;
-                sh.cand_pos[lane] = ~0u;
+                sh.cand_tri[lane] = ~0u;
             }
             __syncwarp();       // the ring slots just read may be rewritten by the next stage-1 round
             RM_PROF_MARK(6);
@@ -943,11 +948,12 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
         RM_PROF_MARK(2);
         // ---- C
         if (state == TS_READY) {
-            if (best_pos != ~0u) {
+            if (best_tri != ~0u) {
                 const double closest = __longlong_as_double((long long)best_t);
-                // the cell's closest hit is the grid's answer; merge with what the other objects found
-                if (closer(closest, a.grid_object, a.hit.t[ray], a.hit.obj[ray])) {
-                    a.hit.t[ray] = closest; a.hit.obj[ray] = a.grid_object; a.hit.sub[ray] = __ldg(&g.refs[best_pos]);
+                // the cell's closest hit is the grid's answer; merge with what the other objects found (the hit record of
+                // this ray as k_setup left it came in with the traversal record: no global read here)
+                if (closer(closest, a.grid_object, sh.best_t[lane], sh.best_obj[lane])) {
+                    a.hit.t[ray] = closest; a.hit.obj[ray] = a.grid_object; a.hit.sub[ray] = best_tri;
                 }
                 state = TS_IDLE;
             } else {
