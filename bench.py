@@ -311,8 +311,8 @@ def bench_ours(args):
                     C_, T_ = cs["cells"][d] / g_, cs["triangle_tests"][d] / g_
                     units, per_unit = d_grid[d], 64.0 + 8.0 * C_ + 76.0 * T_
                     # what THIS kernel has to move for the same decisions: 128-B record + 16-B hit, a 4-B occupancy word per cell, an 8-B record
-                    # per occupied cell, a 16-B bounding sphere per candidate, reference + positions (100 B) per candidate not proven a miss
-                    kernel_bytes[d] = (144.0 + 4.0 * C_ + 8.0 * cs["occupied_cells"][d] / g_ + 16.0 * T_ + 100.0 * cs["evaluated_tests"][d] / g_) * d_grid[d]
+                    # per occupied cell, a 16-B bounding sphere + 4-B triangle index per candidate, the 96-B positions per candidate not proven a miss
+                    kernel_bytes[d] = (144.0 + 4.0 * C_ + 8.0 * cs["occupied_cells"][d] / g_ + 20.0 * T_ + 96.0 * cs["evaluated_tests"][d] / g_) * d_grid[d]
                     survive[d] = cs["evaluated_tests"][d] / max(cs["triangle_tests"][d], 1)
                     # f64 add/sub/mul/div this kernel executes per grid ray: 1 per cell step (t_max += t_delta), 19 per bounding-sphere
                     # pre-test, and the counted exits (20 / 30 / 46 / 52) of the Triangle::intersects calls it evaluates; the reference
@@ -362,7 +362,7 @@ def bench_ours(args):
                                       "achieved_gbs": sum(kernel_bytes.values()) / (pk["ms"] * 1e-3) / 1e9,
                                       "frac_of_hbm_peak": sum(kernel_bytes.values()) / (pk["ms"] * 1e-3) / 1e9 / peak,
                                       "tests_evaluated_fraction": sum(survive.values()) / max(len(survive), 1),
-                                      "what": "bytes this kernel's own algorithm moves per grid ray: 144 + 4 C + 8 C_occupied + 16 T + 100 T_evaluated "
+                                      "what": "bytes this kernel's own algorithm moves per grid ray: 144 + 4 C + 8 C_occupied + 20 T + 96 T_evaluated "
                                               "(the bounding-sphere pre-test proves most of the reference's T triangle tests to be misses without fetching them)"}
                                      if top == "traverse" else None),
                     "traffic_note": "ncu dram bytes per grid ray (360 B, depths 1-3 of a 16-spp batch) x grid rays per launch; far BELOW the algorithmic bytes because the "

@@ -695,7 +695,7 @@ struct TravWarpShared {
     unsigned olane[32];                // q-th lane that contributes a list to the pool
     unsigned odelta[32];               // ... and (first reference of its cell) - (its first item): position = item + odelta
     double2 dd_lim[32];                // |d|^2 of the lane's ray, and the guard of cull_sphere
-    unsigned s_pos[64];                // ring of candidates that survived the sphere pre-test: list position
+    unsigned s_tri[64];                // ring of candidates that survived the sphere pre-test: triangle index
     unsigned char s_owner[64];         // ... and the lane that owns the ray
     double best_t[32];                 // the lane's ray: closest hit among the objects evaluated before this grid (from the
     int best_obj[32];                  // traversal record), merged with the grid's answer when the ray finishes
@@ -872,23 +872,30 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
                 pos = item + sh.odelta[q];
             }
         };
-        // Two stages, both with full lanes.  Stage 1: a round of 32 candidates is located, their bounding spheres (16 B,
-        // contiguous per cell: a coalesced read, fetched one round ahead) tested, and the candidates whose ray provably
-        // misses are dropped; survivors are appended (ballot compaction, order kept) to a ring in shared memory.
-        // Stage 2, whenever 32 survivors wait (or the pool is exhausted): reference -> 96-B record -> Triangle::intersects.
+        // Two stages, both with full lanes.  Stage 1: a round of 32 candidates is located, their bounding spheres and triangle
+        // indices (16 B + 4 B, contiguous per cell: coalesced reads, fetched one round ahead) are read, the spheres tested, and
+        // the candidates whose ray provably misses are dropped; survivors are appended (ballot compaction, order kept) to a ring
+        // in shared memory and their 96-B records start towards L1.
+        // Stage 2, whenever 32 survivors wait (or the pool is exhausted): 96-B record -> Triangle::intersects.
         unsigned owner = 0, pos = 0;
         float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
         locate(0u, owner, pos);
         if (lane < total) sp = __ldg(&g.sphr[pos]);
+        unsigned tri = 0;                                    // ... and its triangle index (same index: one more coalesced read)
+        if (lane < total) tri = __ldg(&g.refs[pos]);
         unsigned base = 0, q_head = 0, q_count = 0;          // warp-uniform
         for (;;) {
             if (base < total && q_count < 32u) {
                 const bool valid = base + lane < total;
-                const unsigned c_owner = owner, c_pos = pos;
+                const unsigned c_owner = owner;
                 const float4 c_sp = sp;
+                const unsigned c_tri1 = tri;
                 if (base + 32u < total) {                    // warp-uniform
                     locate(base + 32u, owner, pos);
-                    if (base + 32u + lane < total) sp = __ldg(&g.sphr[pos]);
+                    if (base + 32u + lane < total) {
+                        sp = __ldg(&g.sphr[pos]);
+                        tri = __ldg(&g.refs[pos]);
+                    }
                 }
                 bool pass = false;
                 if (valid) {
@@ -899,7 +906,11 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
                 const unsigned m = __ballot_sync(FULL, pass);
                 if (pass) {
                     const unsigned slot = (q_head + q_count + __popc(m & lt)) & 63u;
-                    sh.s_pos[slot] = c_pos; sh.s_owner[slot] = (unsigned char)c_owner;
+                    sh.s_tri[slot] = c_tri1; sh.s_owner[slot] = (unsigned char)c_owner;
+                    // the survivor's 96-B record (up to two lines) starts towards L1 now; stage 2 reads it a few rounds later
+                    const double* tp = g.tri + (size_t)c_tri1 * 12;
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(tp));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + 8));
                 }
                 q_count += __popc(m);
                 if (COUNT && pass) n_surv++;
@@ -917,7 +928,7 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
             if (valid) {
                 const unsigned slot = (q_head + lane) & 63u;
                 c_owner = sh.s_owner[slot];
-                c_tri = __ldg(&g.refs[sh.s_pos[slot]]);
+                c_tri = sh.s_tri[slot];
                 const TriPos tp = load_triangle(g.tri + (size_t)c_tri * 12);
                 const double2 r0 = sh.ray[c_owner][0], r1 = sh.ray[c_owner][1], r2 = sh.ray[c_owner][2];
                 double t;
