@@ -57,6 +57,17 @@ def test_reflective_spheres_same_stream():
     assert gs["rays"] > 0.5 * oc["rays"]
 
 
+def test_baseline_config_c1_same_stream():
+    """BASELINE.json configs[0] exactly as given: ReflectiveSpheres, 320x240, 16 spp, 5 bounces, 32x32 tiles (1 228 800 paths)."""
+    objs, cam, spp = F.reflective_spheres(), F.camera(320, 240), 16
+    task = A.render_tiled(product_scene(objs), settings(cam, spp), A.GpuOptions(seed=1))      # the reference-facing call, 80 tiles
+    frame = task.await_()
+    gs = task.stats()
+    o, oc = O.render(oracle_scene(objs), cam, spp, seed=1)
+    compare_same_stream(frame * spp, o, spp, "C1 ReflectiveSpheres 320x240x16")
+    assert gs["samples"] == oc["samples"] == 320 * 240 * 16
+
+
 def test_reflective_spheres_noise_floor():
     """RMSE(GPU, oracle seed A) <= 1.15 RMSE(oracle seed B, oracle seed A) per channel, different streams."""
     objs, cam, spp = F.reflective_spheres(), F.camera(128, 96), 32
