@@ -369,7 +369,7 @@ def bench_ours(args):
                                     "150 MB traversal set is L2-resident and every triangle is fetched by many rays (L2 hit 85-89 %)",
                     "note": "achieved/frac use the REFERENCE algorithm's bytes (SURVEY 8d: 64 + 8 C + 76 T); the kernel makes the same decisions while "
                             "fetching far less (kernel_model), so frac can exceed 1. f64 no-FMA traversal of an L2-resident grid: the binding limits "
-                            "are instruction issue (ncu: 60-68 % issue-active, FP64 pipe 22 %, LSU data pipe 43-50 %) and L2 latency, not HBM "
+                            "are instruction issue (ncu: 66-71 % issue-active, FP64 pipe 22-24 %, LSU data pipe 48-58 %) and L2 latency, not HBM "
                             "(4-7 % of peak); see DESIGN.md section 6 and profiles/"}
     dr.close()
     del dr
