@@ -1,5 +1,4 @@
-// raymond-cuda-sys/src/lib.rs — 1:1 with include/raymond.h (never compiled here: no rustc in the build image)
-// raymond-cuda-sys/src/lib.rs  — 1:1 with include/raymond.h
+// raymond-cuda-sys/src/lib.rs — 1:1 with include/raymond.h, RM_ABI_VERSION 2 (never compiled here: no rustc in the build image)
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
 
@@ -17,7 +16,8 @@ use std::os::raw::{c_char, c_int, c_void};
     pub samples_per_iteration: usize, pub tile_size: [usize; 2], pub bounce_limit: usize }
 #[repr(C)] #[derive(Clone, Copy)] pub struct rm_gpu_options {
     pub device: i32, pub rank: i32, pub world_size: i32, pub partition: u32, pub seed: u64,
-    pub stream: *mut c_void, pub accum_device: *mut c_void, pub batch_spp: usize, pub flags: u32, pub device_count: u32 }
+    pub stream: *mut c_void, pub accum_device: *mut c_void, pub batch_spp: usize, pub flags: u32, pub device_count: u32,
+    pub device_list: *const i32, pub precision: u32, pub reserved: u32 }
 #[repr(C)] pub struct rm_tile { pub sample_count: usize, pub width: usize, pub height: usize, pub left: usize, pub top: usize, pub data: *mut rm_vec3 }
 #[repr(C)] pub struct rm_message { pub kind: u32, pub reserved: u32, pub tile: rm_tile }
 #[repr(C)] #[derive(Default)] pub struct rm_stats {

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RM_ABI_VERSION 1
+#define RM_ABI_VERSION 2
 
 /* ------------------------------------------------------------------ status */
 
@@ -202,6 +202,13 @@ typedef enum rm_partition {
     RM_PARTITION_TILES = 1      /* tiles dealt round-robin in the reference's tile order (src/trace.rs:146-172) */
 } rm_partition;
 
+/* Arithmetic of the STATISTICAL scope (BRDF sampling and weights, src/trace.rs:256-319,362-416).  The bit-exact scope —
+ * camera rays, Scene::intersect, hit points, normals, ray offsets — is always the reference's f64 sequence. */
+typedef enum rm_precision {
+    RM_PRECISION_F64 = 0,       /* every operation is the reference's f64 operation, in its order (same-stream parity with the oracle) */
+    RM_PRECISION_F32_SHADING = 1 /* lobe sampling, Fresnel, GGX and Smith terms in f32 with FMA; agrees with the f64 mode within Monte-Carlo noise */
+} rm_precision;
+
 #define RM_FLAG_KEEP_NONFINITE 1u  /* accumulate NaN/Inf samples like the reference instead of dropping+counting them */
 #define RM_FLAG_STAGE_TIMING 2u    /* bracket every kernel launch with CUDA events; totals per wavefront stage in rm_stage_stats */
 #define RM_FLAG_COUNT_WORK 4u      /* instrumented kernels: count grid cells visited and triangle tests per stage (slower) */
@@ -218,9 +225,15 @@ typedef struct rm_gpu_options {
     void* accum_device;      /* optional caller-owned device buffer, W*H rm_vec3 (f64 sums), zeroed by the library */
     size_t batch_spp;        /* samples per pixel per wavefront batch; 0 = auto */
     uint32_t flags;          /* RM_FLAG_* */
-    uint32_t device_count;   /* rm_render_tiled only: > 1 renders on devices device .. device+device_count-1 from THIS process (one
-                              * driver thread and stream per GPU, `partition` between them) and sums the accumulators onto the first
-                              * device with peer copies over NVLink.  rank / world_size are then set by the library.  0 or 1 = one GPU. */
+    uint32_t device_count;   /* rm_render_tiled only: > 1 renders on `device_count` devices from THIS process (one stream per
+                              * device, `partition` between them); the accumulators are combined over NVLink (every device sums
+                              * its slice of the frame from all peers, in device order) straight into the frame the caller reads.
+                              * rank / world_size are then set by the library.  0 or 1 = one GPU. */
+    const int32_t* device_list; /* the `device_count` CUDA ordinals to use; NULL = device, device+1, ...  An ordinal may appear more
+                              * than once (several shares of the frame rendered on one GPU: same data path — scene clone, peer
+                              * reduce, progressive tiles — on a box with fewer GPUs). */
+    uint32_t precision;      /* rm_precision */
+    uint32_t reserved;
 } rm_gpu_options;
 
 /* Tile { sample_count, width, height, left, top, data }   core/src/tile.rs:6-14

@@ -50,6 +50,8 @@ PARTITION_TILES = 1
 FLAG_KEEP_NONFINITE = 1
 FLAG_STAGE_TIMING = 2
 FLAG_COUNT_WORK = 4
+PRECISION_F64 = 0
+PRECISION_F32_SHADING = 1
 STAGE_SLOTS = 16
 
 
@@ -82,7 +84,8 @@ class SettingsC(C.Structure):
 
 class GpuOptionsC(C.Structure):
     _fields_ = [("device", C.c_int32), ("rank", C.c_int32), ("world_size", C.c_int32), ("partition", C.c_uint32), ("seed", C.c_uint64),
-                ("stream", C.c_void_p), ("accum_device", C.c_void_p), ("batch_spp", C.c_size_t), ("flags", C.c_uint32), ("device_count", C.c_uint32)]
+                ("stream", C.c_void_p), ("accum_device", C.c_void_p), ("batch_spp", C.c_size_t), ("flags", C.c_uint32), ("device_count", C.c_uint32),
+                ("device_list", C.POINTER(C.c_int32)), ("precision", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class TileC(C.Structure):
@@ -485,10 +488,19 @@ class GpuOptions:
     batch_spp: int = 0
     flags: int = 0
     device_count: int = 0     # render_tiled only: > 1 = that many GPUs driven from this process
+    device_list: Optional[Sequence[int]] = None   # the ordinals to use (may repeat one); None = device, device+1, ...
+    precision: int = PRECISION_F64
 
     def _c(self) -> GpuOptionsC:
-        return GpuOptionsC(self.device, self.rank, self.world_size, self.partition, self.seed, self.stream or None, self.accum_device or None,
-                           self.batch_spp, self.flags, self.device_count)
+        count = self.device_count
+        lst = None
+        if self.device_list is not None:
+            count = len(self.device_list)
+            lst = (C.c_int32 * max(count, 1))(*[int(d) for d in self.device_list])
+        o = GpuOptionsC(self.device, self.rank, self.world_size, self.partition, self.seed, self.stream or None, self.accum_device or None,
+                        self.batch_spp, self.flags, count, lst, self.precision, 0)
+        o._keep = lst            # the array must outlive the call that reads the struct
+        return o
 
 
 def tile_layout(settings: Settings) -> np.ndarray:

@@ -184,6 +184,16 @@ rm_task* rm_render_tiled(const rm_scene* scene, const rm_settings* settings, con
         delete t;
         return nullptr;
     }
+    if (G > 1024) {
+        fail(RM_ERR_INVALID_ARGUMENT, "rm_render_tiled: device_count > 1024");
+        delete t;
+        return nullptr;
+    }
+    // the ordinals this task renders on (the caller's list is only read here; an ordinal may repeat)
+    std::vector<int32_t> devices(G);
+    for (size_t g = 0; g < G; g++) devices[g] = (t->options.device_list && t->options.device_count >= 1) ? t->options.device_list[g] : t->options.device + (int32_t)g;
+    t->options.device_list = nullptr;
+    t->options.device = devices[0];
     // scene upload happens here, before the call returns, so a bad scene or a missing GPU is reported synchronously;
     // the device copies are the snapshot (the caller may destroy `scene`).  The first GPU gets the scene from the host
     // (flatten + one H2D copy); every other GPU gets a device-to-device copy of it, one host thread per GPU.
@@ -192,7 +202,8 @@ rm_task* rm_render_tiled(const rm_scene* scene, const rm_settings* settings, con
     std::vector<std::string> errors(G);
     auto options_for = [&](size_t g) {
         rm_gpu_options o = t->options;
-        if (G > 1) { o.device = t->options.device + (int32_t)g; o.rank = (int32_t)g; o.world_size = (int32_t)G; }
+        o.device = devices[g];
+        if (G > 1) { o.rank = (int32_t)g; o.world_size = (int32_t)G; }
         o.device_count = 0;
         return o;
     };

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in declared if not hasattr(L, n)]
     assert not missing, f"libraymond_cuda.so does not export {missing}"
     assert sorted(A.ABI_SYMBOLS) == declared, "api.ABI_SYMBOLS and include/raymond.h disagree"
-    assert L.rm_abi_version() == 1
+    assert L.rm_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header():
