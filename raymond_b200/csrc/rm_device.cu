@@ -29,27 +29,56 @@ static int sm_count(int device) {
     return n > 0 ? n : 148;
 }
 
-// ---- device memory: stream-ordered allocations from the device's default pool with the release threshold lifted,
-// so the multi-GB wavefront queues of one render are handed to the next one instead of being unmapped and
-// re-mapped (cudaFree / cudaMalloc of 10 GB cost 0.1-0.5 s each).  All pool traffic is ordered on the legacy
-// default stream; users synchronise their own stream before dev_free().
-static cudaError_t dev_malloc_raw(void** p, size_t bytes) {
-    static std::mutex mu;
-    static std::vector<int> ready;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        if (std::find(ready.begin(), ready.end(), dev) == ready.end()) {
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-                unsigned long long keep = ~0ull;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            }
-            ready.push_back(dev);
-        }
+// ---- device memory: stream-ordered allocations from a PRIVATE pool per device (the device's default pool, which torch and
+// other libraries in the process may use, is left alone).  The pool keeps up to kPoolKeepBytes of freed memory mapped, so the
+// multi-GB wavefront queues of one render are handed to the next one instead of being unmapped and re-mapped (cudaFree /
+// cudaMalloc of 10 GB cost 0.1-0.5 s each); anything beyond that goes back to the driver at the next synchronisation, and
+// rm_release_cached_memory() returns all of it.  Peers that can reach the device get read/write access to the pool: the
+// accumulator exchange of a multi-GPU task reads peer accumulators directly over NVLink.  All pool traffic is ordered on
+// the legacy default stream; users synchronise their own stream before dev_free().
+namespace {
+constexpr unsigned long long kPoolKeepBytes = 48ull << 30;
+std::mutex g_pool_mu;
+std::map<int, cudaMemPool_t> g_pools;
+}  // namespace
+
+static cudaError_t device_pool(int dev, cudaMemPool_t* out) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    auto it = g_pools.find(dev);
+    if (it != g_pools.end()) { *out = it->second; return cudaSuccess; }
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool = nullptr;
+    cudaError_t e = cudaMemPoolCreate(&pool, &props);
+    if (e != cudaSuccess) return e;
+    unsigned long long keep = kPoolKeepBytes;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    int count = 0;
+    cudaGetDeviceCount(&count);
+    for (int peer = 0; peer < count; peer++) {
+        int can = 0;
+        if (peer == dev || cudaDeviceCanAccessPeer(&can, peer, dev) != cudaSuccess || !can) continue;
+        cudaMemAccessDesc desc{};
+        desc.location.type = cudaMemLocationTypeDevice;
+        desc.location.id = peer;
+        desc.flags = cudaMemAccessFlagsProtReadWrite;
+        cudaMemPoolSetAccess(pool, &desc, 1);
     }
-    cudaError_t e = cudaMallocAsync(p, std::max<size_t>(bytes, 32), 0);
+    cudaGetLastError();
+    g_pools[dev] = pool;
+    *out = pool;
+    return cudaSuccess;
+}
+
+static cudaError_t dev_malloc_raw(void** p, size_t bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    cudaMemPool_t pool = nullptr;
+    if (e == cudaSuccess) e = device_pool(dev, &pool);
+    if (e == cudaSuccess) e = cudaMallocFromPoolAsync(p, std::max<size_t>(bytes, 32), pool, 0);
     if (e == cudaSuccess) e = cudaStreamSynchronize(0);
     return e;
 }
@@ -161,9 +190,11 @@ struct rm_device_scene {
     std::mutex query_mu;
     IntersectBuffers query;
     unsigned* query_counters = nullptr;     // {traversal records, traversal cursor}
+    cudaEvent_t query_done = nullptr;       // end of the last query: the next one (on whatever stream) waits for it before it reuses the scratch
     ~rm_device_scene() {
         cudaSetDevice(device);
         cudaDeviceSynchronize();            // queries may still be running on the caller's streams
+        if (query_done) cudaEventDestroy(query_done);
         for (void* p : allocations) dev_free(p);
         query.release();
         dev_free(query_counters);
@@ -188,6 +219,7 @@ static int upload_grid(rm_device_scene* ds, const Grid& g, DevGrid* out) {
     for (int a = 0; a < 3; a++) d.res[a] = (int)g.resolution[a];
     const double ex = d.bmax[0] - d.bmin[0], ey = d.bmax[1] - d.bmin[1], ez = d.bmax[2] - d.bmin[2];
     d.diag2 = ex * ex + ey * ey + ez * ez;
+    d.diag = std::sqrt(d.diag2);
     d.n_cells = g.n_cells();
     const size_t nc = (size_t)d.n_cells, nt = g.triangles.size(), nr = g.references.size();
     const size_t n_occ = (nc + 31) / 32;
@@ -768,6 +800,9 @@ int rm_device_scene_intersect(rm_device_scene* ds, const rm_ray* rays, size_t co
         if (int st = ds->query.alloc(count)) return st;
     }
     if (!ds->query_counters) RM_CUDA(dev_malloc(&ds->query_counters, 2 * sizeof(unsigned)));
+    // one scratch set per device scene: calls on different streams are ordered one after the other on the device
+    if (!ds->query_done) RM_CUDA(cudaEventCreateWithFlags(&ds->query_done, cudaEventDisableTiming));
+    else RM_CUDA(cudaStreamWaitEvent(stream, ds->query_done, 0));
     RM_CUDA(cudaMemsetAsync(ds->query_counters, 0, 2 * sizeof(unsigned), stream));
     RenderParams rp{};
     SetupArgs sa{};
@@ -780,6 +815,7 @@ int rm_device_scene_intersect(rm_device_scene* ds, const rm_ray* rays, size_t co
     const size_t blocks = std::min<size_t>((count + kBlock - 1) / kBlock, (size_t)ds->sms * 32);
     k_export_hits<<<(unsigned)blocks, kBlock, 0, stream>>>(ds->query.hit, count, (long long*)obj, (unsigned long long*)sub, distance);
     RM_CUDA(cudaGetLastError());
+    RM_CUDA(cudaEventRecord(ds->query_done, stream));
     return RM_OK;
 }
 
@@ -1035,9 +1071,13 @@ int rm_release_cached_memory(void) {
     int current = 0;
     if (count) cudaGetDevice(&current);
     for (int d = 0; d < count; d++) {
-        cudaMemPool_t pool;
-        if (cudaSetDevice(d) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess)
-            cudaMemPoolTrimTo(pool, 0);
+        cudaMemPool_t pool = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(g_pool_mu);
+            auto it = g_pools.find(d);
+            if (it != g_pools.end()) pool = it->second;
+        }
+        if (pool && cudaSetDevice(d) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
         cudaGetLastError();
     }
     if (count) cudaSetDevice(current);

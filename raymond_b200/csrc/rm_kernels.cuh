@@ -54,7 +54,8 @@ struct DevGrid {
     double bmin[3], bmax[3], cell[3];
     int res[3];
     int pad;
-    double diag2;             // squared diagonal of the bounding box (bounds the size of any triangle edge)
+    double diag2;             // squared diagonal of the bounding box (bounds the squared length of any triangle edge)
+    double diag;              // ... and the diagonal (bounds the distance between any two points of the box)
     unsigned long long n_cells;
     const uint2* cells;
     const unsigned* occ;
@@ -621,10 +622,11 @@ __global__ void __launch_bounds__(kBlock, RM_SETUP_BLOCKS_PER_SM) k_setup(const 
                 // Every triangle lies inside the box, so the true distance of any grid hit is >= the box
                 // entry distance.  If another object is already hit before the entry point by more than the
                 // worst-case error of a computed triangle distance, the grid cannot win the strict `<` of
-                // Scene::intersect and its traversal is skipped.  Error bound of Moller-Trumbore's t:
-                // eps * |o - v0| * |e|^2 / |a| with |a| >= 1e-8 (triangle.rs:21), |o - v0| <= tmax (|d| = 1),
-                // |e|^2 <= diag2  =>  <= 1.2e-8 * tmax * diag2; the margin below is 10x that plus 1e-6.
-                if (push && best_obj >= 0 && tmin > best_t + (1e-6 + 1e-7 * fabs(tmax) * g.diag2)) push = false;
+                // Scene::intersect and its traversal is skipped.  Error bound of Moller-Trumbore's t = f * dot(e2, cross(s, e1)):
+                // c * eps * |s| * |e|^2 / |a| with |a| >= 1e-8 (triangle.rs:21), c * eps <= 4e-15, |e|^2 <= diag2 and
+                // |s| = |o - v0| <= max(tmin, 0) + diag (v0 is in the box; the box is entered at distance max(tmin, 0), |d| = 1)
+                // =>  <= 4e-7 * (max(tmin, 0) + diag) * diag2; plus 1e-6 absolute for the rounding of tmin itself.
+                if (push && best_obj >= 0 && tmin > best_t + (1e-6 + 4e-7 * (fmax(tmin, 0.0) + g.diag) * g.diag2)) push = false;
             }
         }
         const unsigned mask = __ballot_sync(0xffffffffu, push);

@@ -48,6 +48,26 @@ def _worker(rank: int, world: int, port: int, mode: str, out_dir: str):
             for (l, t, w, h), o in zip(layout, owner):
                 if o == rank:
                     sums[t:t + h, l:l + w] = full[t:t + h, l:l + w]
+        if mode == "progressive":
+            # two passes accumulate into the rank's own running sums; a checkpoint after each, and nothing is cleared in between
+            # (TileProgressed semantics, src/trace.rs:207-219): the exchange must not disturb any rank's accumulator
+            acc = torch.zeros((48, 64, 3), dtype=torch.float64)
+            ex = D.AccumulatorExchange(acc)
+            shots = []
+            for done, n in ((0, 2), (2, 3)):
+                first, count, stride = D.sample_share(n, rank, world)
+                if count:
+                    part, _ = O.render(sc, cam, count, seed=seed, first_sample=done + first, sample_stride=stride, worker_count=2)
+                    acc += torch.from_numpy(part)
+                before = acc.clone()
+                total = ex.checkpoint(acc, 0)
+                assert torch.equal(acc, before), "a checkpoint modified the rank's own running sums"
+                assert (total is None) == (rank != 0)
+                if rank == 0:
+                    shots.append(total.numpy().copy())
+            if rank == 0:
+                np.save(os.path.join(out_dir, "progressive.npy"), np.stack(shots))
+            return
         acc = torch.from_numpy(sums.copy())
         D.reduce_sums(acc, 0)
         if rank == 0:
@@ -69,6 +89,39 @@ def test_two_rank_partition_and_reduce(tmp_path, mode):
         assert np.array_equal(got, want)                     # disjoint tiles: the sum is exact
     else:
         assert np.allclose(got, want, rtol=1e-12, atol=1e-12)   # same samples, different association
+
+
+def test_two_rank_progressive_checkpoints_do_not_double_count(tmp_path):
+    """Two passes, a checkpoint after each, no clear() in between: checkpoint k is the 1-rank image of the samples so far."""
+    from oracle import oracle as O
+    from raymond_b200 import fixtures as F
+    from util import oracle_scene
+    mp.spawn(_worker, args=(2, _free_port(), "progressive", str(tmp_path)), nprocs=2, join=True)
+    shots = np.load(tmp_path / "progressive.npy")
+    sc, cam = oracle_scene(F.reflective_spheres()), F.camera(64, 48)
+    first2, _ = O.render(sc, cam, 2, seed=17)
+    all5, _ = O.render(sc, cam, 5, seed=17)
+    assert np.allclose(shots[0], first2, rtol=1e-12, atol=1e-12)
+    assert np.allclose(shots[1], all5, rtol=1e-12, atol=1e-12)
+
+
+def test_slice_tiles_is_the_reference_message_sequence():
+    from raymond_b200 import api as A
+    from raymond_b200 import distributed as D
+    from raymond_b200 import fixtures as F
+    from util import settings
+    st = settings(F.camera(70, 50), 3, tile=(32, 32))
+    layout = A.tile_layout(st)
+    sums = np.arange(50 * 70 * 3, dtype=np.float64).reshape(50, 70, 3)
+    msgs = list(D.slice_tiles(sums, layout, "TileProgressed", 2))
+    assert [(m.tile.left, m.tile.top, m.tile.width, m.tile.height) for m in msgs] == [tuple(r) for r in layout]
+    assert [(m.tile.left, m.tile.top) for m in msgs[:3]] == [(0, 0), (0, 32), (32, 0)]      # y advances first (src/trace.rs:146-172)
+    for m in msgs:
+        t = m.tile
+        assert m.kind == "TileProgressed" and t.sample_count == 2
+        assert np.array_equal(t.data, sums[t.top:t.top + t.height, t.left:t.left + t.width])
+    own = D.tile_owner(len(layout), 2) == 1
+    assert len(list(D.slice_tiles(sums, layout, "TileFinished", 3, owned=own))) == int(own.sum())
 
 
 def test_sample_share_covers_every_sample_once():

@@ -182,3 +182,34 @@ def test_fp64_rate_probe_is_plausible():
     """rm_measure_fp64_rate: a B200 has 148 SMs x 64 f64 lanes; without FMA that is ~18.6 Tera-op/s at 1.965 GHz."""
     g = A.measure_fp64_rate(0)
     assert 5e3 < g < 4e4, g
+
+
+def test_grid_skip_margin_on_a_large_box_with_grazing_rays():
+    """k_setup skips a grid traversal when an analytic object is hit before the grid's box is entered, by a margin that bounds
+    the rounding error of a computed triangle distance (|o - v0| <= max(tmin, 0) + diagonal).  A 2000-unit box holding slivers
+    whose |a| is close to Triangle::intersects' 1e-8 threshold, a sphere grazing the box surface and rays that clip the box
+    corners (small tmax - tmin, far v0): the skip must never change which object Scene::intersect reports."""
+    rng = np.random.default_rng(5)
+    big = F.translate(F.bumpy_sphere(24, 48, 900.0, 0.1, (1.0, 0.9, 0.6)), (0.0, 0.0, 2500.0))
+    # near-degenerate slivers: long thin triangles scattered through the box
+    n = 4000
+    c = rng.uniform(-800, 800, (n, 3)) * np.array([1.0, 1.0, 0.4]) + np.array([0.0, 0.0, 2500.0])
+    e1 = rng.normal(size=(n, 3)) * np.array([300.0, 300.0, 60.0])      # res.y >= res.z: the only regime the reference's cell index survives (A1)
+    e2 = e1 * rng.uniform(0.2, 0.9, (n, 1)) + rng.normal(size=(n, 3)) * rng.choice([1e-6, 1e-4, 1e-2], (n, 1))
+    sliv = F.make_triangles(c, c + e1, c + e2)
+    tris = np.concatenate([big, sliv])
+    lo, hi = F.positions(tris).reshape(-1, 3).min(axis=0), F.positions(tris).reshape(-1, 3).max(axis=0)
+    objs = [("sphere", (lo[0] - 40.0, 0.0, 2500.0), 39.999, ("Diffuse", (0.8, 0.2, 0.2), 0.5)),        # grazes the box's -x face
+            ("sphere", (0.0, 0.0, 1200.0), 300.0, ("Metal", (0.2, 0.2, 0.9), 0.1)),                     # in front of the box
+            ("grid", tris, F.DRAGON_MATERIAL),
+            ("plane", (0.0, lo[1] - 1e-3, 0.0), (0.0, 1.0, 0.0), ("Diffuse", (0.5, 0.5, 0.5), 0.5))]    # just under the box
+    m = 200_000
+    corners = np.array([[x, y, z] for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])])
+    target = corners[rng.integers(0, 8, m)] + rng.normal(size=(m, 3)) * rng.choice([1e-3, 1.0, 50.0], (m, 1))
+    origin = rng.uniform(-3000, 3000, (m, 3)) + np.array([0.0, 1500.0, 0.0])
+    d = target - origin
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([np.concatenate([origin, d], axis=1), O.primary_rays(F.camera(320, 200))])
+    want = oracle_scene(objs).intersect(rays, threads=8)
+    assert {0, 1, 2, 3} <= set(want[0].tolist())
+    assert_hits_equal(product_scene(objs).intersect(rays), want, "large box, grazing rays")
