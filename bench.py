@@ -9,9 +9,13 @@ Scene::intersect (sphere / planes / uniform-grid DDA), the BRDF bounce loop and 
 Metric: Msamples/s (paths per second, whole job).  The dragon mesh is missing from the reference
 snapshot, so the scene uses the documented STAND-IN mesh (raymond_b200.fixtures.dragon_standin).
 
-N > 1 (torchrun, one rank per GPU): weak scaling — every rank renders `spp` samples per pixel of the
-same frame (global sample indices interleaved, rank g takes g, g+N, ...), then the per-rank f64
-accumulators are summed onto rank 0 with an NCCL reduce inside the timed region.
+N > 1 (torchrun, one rank per GPU): STRONG scaling — the job stays the 1920x1080 x 500 spp frame; rank g renders
+the global samples g, g+N, ... of every pixel and the per-rank f64 accumulators are summed onto rank 0 with an
+NCCL reduce inside the timed region.  `e2e` is the same frame through the reference-facing call with host buffers:
+render_tiled(scene, settings).await() — at N > 1 with rm_gpu_options.device_count = N, i.e. ONE process (rank 0)
+driving the N GPUs through the C ABI, which is what a Rust caller of the FFI crate gets; the one-process-per-GPU
+variant of the same frame is reported beside it as `e2e_torchrun`.  BASELINE configs[2] and configs[4] are timed at
+the same N in `other_configs`.
 
 One JSON line on stdout (rank 0).
 """
@@ -31,13 +35,9 @@ import numpy as np
 
 METRIC = "Msamples/sec (paths x 5 bounces), GoldDragon 1920x1080 500 spp"
 UNIT = "Msamples/s"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, from the ncu --set full capture in profiles/ (None = not captured)
-NCU_TRAFFIC_PER_UNIT = {
-    # profiles/r1_v10_traverse_ncu_summary.md: the k_traverse launches of depth 1, 2, 3 of one 16-spp batch (20.9 M grid rays)
-    # read + wrote 2.11 + 3.48 + 1.94 GB of DRAM = 360 B per grid ray
-    "k_traverse": 360.0,
-}
-
+# Per-unit constants of the dominant kernel taken from the ncu --set full capture under profiles/ (dram bytes, warp instructions, ...):
+# written by scripts/ncu_constants.py from the .ncu-rep and the bench line of the same command, never edited by hand.
+NCU_CONSTANTS = os.path.join(ROOT, "profiles", "ncu_constants.json")
 
 print_line = None
 
@@ -58,9 +58,14 @@ def parse_args():
     p.add_argument("--bounces", type=int, default=5)
     p.add_argument("--scene", default="gold_dragon", choices=["gold_dragon", "reflective_spheres", "reflective_spheres_dof"])
     p.add_argument("--seed", type=int, default=2026)
+    p.add_argument("--precision", default="f64", choices=["f64", "f32shade"],
+                   help="arithmetic of the statistical scope (BRDF sampling / weights); the intersection code is always the reference's f64 sequence")
     p.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-extras", action="store_true", help="skip BASELINE configs[2] / configs[4] (other_configs)")
+    p.add_argument("--c3-spp", type=int, default=1000, help="samples of the configs[2] run in other_configs (tests shrink it)")
+    p.add_argument("--c5-spp", type=int, default=4096, help="samples of the configs[4] run in other_configs (tests shrink it)")
     return p.parse_args()
 
 
@@ -78,6 +83,16 @@ def camera_for(args):
     if args.scene == "reflective_spheres_dof":
         return F.camera(args.width, args.height, focal_length=2.5, aperture_radius=0.5)
     return F.camera(args.width, args.height)
+
+
+def config_of(args, label):
+    """The workload description — the SAME dict from both arms (what each arm actually sampled goes into cpu_baseline.sample)."""
+    return {"workload": f"{label} {args.width}x{args.height}, {args.spp} spp, {args.bounces} bounces", "scene": args.scene,
+            "width": args.width, "height": args.height, "spp": args.spp, "bounces": args.bounces, "tile": [32, 32],
+            "mesh": "stand-in" if args.scene == "gold_dragon" else "analytic",
+            "parallelism": f"sample-split x{args.gpus} + ncclReduce(sum)" if args.gpus > 1 else "1 GPU",
+            "l2": "inputs exceed L2 (scene ~290 MB + ~10 GB of wavefront queues per 16-spp batch); no explicit flush",
+            "precision": args.precision}
 
 
 # ------------------------------------------------------------------------------- clocks
@@ -192,12 +207,12 @@ def bench_reference(args):
         n += cnt["samples"]
     dt = time.perf_counter() - t0
     value = n / dt / 1e6
-    sample = f"{cam['width']}x{cam['height']} x {spp} spp per step (full frame, reduced spp; the rate is spp-invariant)"
+    sample = (f"each step = {cam['width']}x{cam['height']} x {spp} spp of the workload's frame on {cores} host threads (the full frame at reduced spp: "
+              f"Msamples/s does not depend on spp); f64, -ffp-contract=off, the reference's threading model")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": f"{label} {args.width}x{args.height}, {args.spp} spp, {args.bounces} bounces",
-                                        "scene": args.scene, "spp": args.spp, "bounces": args.bounces, "tile": [32, 32]},
+        "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config_of(args, label),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -207,6 +222,128 @@ def bench_reference(args):
 
 # ------------------------------------------------------------------------------- GPU arm
 
+def ncu_constants(kernel: str):
+    try:
+        return json.load(open(NCU_CONSTANTS)).get(kernel)
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def roofline_record(A, args, scene, settings, local, world, st0, st1, samples_rank0, clocks):
+    """Roofline of the dominant kernel on rank 0: live CUDA-event time per (kernel, depth) over the timed region; algorithmic
+    bytes / operations from an instrumented pass of the same rays (C cells visited, T triangle tests); DRAM bytes, warp
+    instructions and cache hit rates per unit from the ncu capture under profiles/ (profiles/ncu_constants.json)."""
+    W, H = args.width, args.height
+    kinds = A.KERNEL_KINDS
+    d_ms = {k: [b - a for a, b in zip(st0["ms"][k], st1["ms"][k])] for k in kinds}
+    d_launch = {k: [b - a for a, b in zip(st0["launches"][k], st1["launches"][k])] for k in kinds}
+    d_rays = [b - a for a, b in zip(st0["rays"], st1["rays"])]
+    d_grid = [b - a for a, b in zip(st0["grid_rays"], st1["grid_rays"])]
+    d_shtri = [b - a for a, b in zip(st0["shaded_triangles"], st1["shaded_triangles"])]
+    counted = A.Renderer(scene, A.Settings(settings.camera_settings, 4, (32, 32), args.bounces),
+                         A.GpuOptions(device=local, seed=args.seed, flags=A.FLAG_COUNT_WORK, batch_spp=4, precision=PRECISIONS[args.precision]))
+    counted.render(0, 4)
+    cs = counted.stage_stats()
+    counted.close()
+    total_ms = sum(sum(v) for v in d_ms.values())
+    stages, per_kernel = [], {}
+    kernel_bytes, kernel_flops = 0.0, 0.0
+    for d in range(0, A.STAGE_SLOTS):
+        for k in kinds:
+            if d_launch[k][d] == 0:
+                continue
+            C_ = T_ = None
+            if k == "accumulate":
+                # reads 24 B per path, reads + writes 24 B per pixel per batch
+                units, per_unit = samples_rank0, 24.0 + 48.0 * W * H * d_launch[k][d] / max(samples_rank0, 1)
+            elif k == "setup":
+                # ray in (48 B; depth 1 generates it and writes it instead) + hit record out (16 B) + a 128-B traversal record per grid ray
+                units = d_rays[d]
+                per_unit = 48.0 + 16.0 + 128.0 * d_grid[d] / max(d_rays[d], 1)
+            elif k == "traverse":
+                # SURVEY 8d: B(ray) = 64 + 8 C + 76 T  (48-B ray in, 16-B hit out, 8 B per visited cell, 4 + 72 B per triangle test)
+                g_ = max(cs["grid_rays"][d], 1)
+                C_, T_ = cs["cells"][d] / g_, cs["triangle_tests"][d] / g_
+                units, per_unit = d_grid[d], 64.0 + 8.0 * C_ + 76.0 * T_
+                # what THIS kernel has to move for the same decisions: 128-B record + 16-B hit, a 4-B occupancy word per cell, an 8-B record
+                # per occupied cell, a 16-B bounding sphere + 4-B triangle index per candidate, the 96-B positions per candidate not proven a miss
+                kernel_bytes += (144.0 + 4.0 * C_ + 8.0 * cs["occupied_cells"][d] / g_ + 20.0 * T_ + 96.0 * cs["evaluated_tests"][d] / g_) * d_grid[d]
+                # f64 add/sub/mul/div this kernel executes per grid ray: 1 per cell step (t_max += t_delta), 19 per bounding-sphere
+                # pre-test, and the counted exits (20 / 30 / 46 / 52) of the Triangle::intersects calls it evaluates
+                kernel_flops += (C_ + 19.0 * T_ + cs["evaluated_test_flops"][d] / g_) * d_grid[d]
+            else:
+                # shade (+ the next depth's set-up when fused): ray + throughput + id + hit in (92 B), next ray out (76 B) or radiance out (24 B);
+                # +144 B (positions, normals) per shaded triangle
+                units = d_rays[d]
+                cont = d_rays[d + 1] if d + 1 < A.STAGE_SLOTS and d < args.bounces else 0
+                per_unit = 92.0 + (76.0 * cont + 24.0 * (d_rays[d] - cont) + 144.0 * d_shtri[d]) / max(d_rays[d], 1)
+            bytes_total = per_unit * units
+            ms_ = d_ms[k][d]
+            stages.append({"kernel": "k_" + k, "depth": d, "ms": ms_, "launches": d_launch[k][d], "units": units,
+                           "alg_bytes_per_unit": per_unit, "cells_per_ray": C_, "tests_per_ray": T_,
+                           "achieved_gbs": bytes_total / (ms_ * 1e-3) / 1e9 if ms_ > 0 else None, "share": ms_ / max(total_ms, 1e-9)})
+            pk = per_kernel.setdefault(k, {"ms": 0.0, "launches": 0, "bytes": 0.0, "units": 0})
+            pk["ms"] += ms_; pk["launches"] += d_launch[k][d]; pk["bytes"] += bytes_total; pk["units"] += units
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    top = max(per_kernel, key=lambda k: per_kernel[k]["ms"])
+    pk = per_kernel[top]
+    secs = pk["ms"] * 1e-3
+    hbm_ach = pk["bytes"] / secs / 1e9 if secs > 0 else 0.0
+    nc = ncu_constants("k_" + top) or {}
+    sms = 148
+    try:
+        import torch
+        sms = torch.cuda.get_device_properties(local).multi_processor_count
+    except Exception:  # noqa: BLE001
+        pass
+    mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
+    issue_peak = sms * 4 * mhz * 1e6 / 1e9                        # one warp instruction per scheduler per clock, G warp-inst/s
+    rec = {"kernel": "k_" + top, "unit_name": "grid ray" if top == "traverse" else ("path" if top == "accumulate" else "ray"),
+           "launch_ms_avg": pk["ms"] / max(pk["launches"], 1), "launches": pk["launches"], "share_of_step": pk["ms"] / max(total_ms, 1e-9),
+           "units_per_launch": pk["units"] / max(pk["launches"], 1)}
+    for k, v in per_kernel.items():
+        rec["share_k_" + k] = v["ms"] / max(total_ms, 1e-9)
+    # --- the HBM roofline the contract defines: ALGORITHMIC bytes of the reference's algorithm / time / measured copy bandwidth
+    rec.update({"hbm_achieved_gbs": hbm_ach, "hbm_peak_gbs": hbm_peak, "hbm_frac": hbm_ach / hbm_peak, "hbm_peak_source": hbm_src,
+                "alg_bytes_per_unit": pk["bytes"] / max(pk["units"], 1), "alg_bytes_per_launch": pk["bytes"] / max(pk["launches"], 1)})
+    traffic = None
+    if nc.get("dram_bytes_per_unit") is not None:
+        traffic = nc["dram_bytes_per_unit"] * pk["units"] / max(pk["launches"], 1)
+        rec["dram_bytes_per_unit_ncu"] = nc["dram_bytes_per_unit"]
+        rec["dram_frac"] = nc["dram_bytes_per_unit"] * pk["units"] / secs / 1e9 / hbm_peak     # real DRAM traffic against the HBM peak
+    if top == "traverse":
+        rec["kernel_bytes_per_unit"] = kernel_bytes / max(pk["units"], 1)
+        rec["kernel_bytes_frac_of_hbm"] = kernel_bytes / secs / 1e9 / hbm_peak
+        fp64_peak = A.measure_fp64_rate(local)
+        rec.update({"fp64_peak_gops": fp64_peak, "fp64_achieved_gops": kernel_flops / secs / 1e9, "fp64_frac": kernel_flops / secs / 1e9 / fp64_peak,
+                    "fp64_ops_per_unit": kernel_flops / max(pk["units"], 1)})
+    for key in ("l1_hit", "l2_hit", "threads_per_inst", "fp64_pipe_active", "issue_active_ncu", "registers", "source"):
+        if key in nc:
+            rec["ncu_" + key] = nc[key]
+    # --- which ceiling binds.  The traversal set is L2-resident (DRAM at a few % of peak) and the arithmetic is 0.1 of the f64 rate:
+    # the largest fraction is instruction issue, so that is the roofline reported in bound / achieved / peak / frac.
+    if nc.get("warp_inst_per_unit") is not None:
+        inst_ach = nc["warp_inst_per_unit"] * pk["units"] / secs / 1e9
+        rec.update({"bound": "issue", "achieved": inst_ach, "peak": issue_peak, "unit": "Gwarp-inst/s", "frac": inst_ach / issue_peak,
+                    "warp_inst_per_unit_ncu": nc["warp_inst_per_unit"],
+                    "peak_source": f"{sms} SMs x 4 schedulers x {mhz:.0f} MHz (median SM clock sampled during the timed region), 1 warp instruction per scheduler per clock",
+                    "note": "binding ceiling = instruction issue: warp instructions per unit (ncu smsp__inst_executed of the same kernel, profiles/) x units / live kernel time; "
+                            "the contract's HBM roofline on algorithmic bytes is in hbm_achieved_gbs / hbm_peak_gbs / hbm_frac, real DRAM traffic in dram_frac, arithmetic in fp64_frac"})
+    else:
+        rec.update({"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak, "peak_source": hbm_src})
+    rec["traffic"] = traffic
+    return rec, stages
+
+
+PRECISIONS = {"f64": 0, "f32shade": 1}
+
+
 def bench_ours(args):
     import torch
     import torch.distributed as dist
@@ -214,6 +351,7 @@ def bench_ours(args):
     from raymond_b200 import api as A
     from raymond_b200 import build as B
     from raymond_b200 import distributed as D
+    from raymond_b200 import fixtures as F
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -221,11 +359,12 @@ def bench_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — this implementation has no CPU path")
     torch.cuda.set_device(local)
+    side = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL would print its banner on stdout, next to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        side = dist.new_group(backend="gloo")      # host-side waits (while rank 0 alone drives all GPUs) must not spin on the devices
     B.build()
+    precision = PRECISIONS[args.precision]
 
     objs, label = scene_objects(args.scene)
     cam = camera_for(args)
@@ -233,18 +372,35 @@ def bench_ours(args):
     t0 = time.perf_counter()
     scene = A.Scene.from_fixture(objs)                   # host side: Mesh::new + AccGrid::build_from_mesh
     host_build_s = time.perf_counter() - t0
-    settings = A.Settings(A.CameraSettings.from_fixture(cam), spp * world, (32, 32), args.bounces)
+    settings = A.Settings(A.CameraSettings.from_fixture(cam), spp, (32, 32), args.bounces)
 
     def barrier():
         if world > 1:
             dist.barrier()
 
-    # ---- resident-scene throughput (`value`): scene in HBM, accumulator in HBM, NCCL reduce included
-    dr = D.DistributedRenderer(scene, settings, device=local, seed=args.seed, flags=A.FLAG_STAGE_TIMING)
-    total_spp = spp * world                               # weak scaling: per-GPU work fixed
+    def host_barrier():
+        if world > 1:
+            dist.barrier(group=side)
+
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- resident-scene throughput (`value`): scene in HBM, accumulators in HBM, this rank's share of the 500 samples, then the
+    #      accumulator exchange (copy + ncclReduce onto rank 0) — all inside the timed region
+    dr = D.DistributedRenderer(scene, settings, device=local, seed=args.seed, flags=A.FLAG_STAGE_TIMING, precision=precision)
     for _ in range(args.warmup):
         dr.clear()
-        dr.render(total_spp)
+        dr.render(spp)
+        dr.checkpoint()
     dr.synchronize()
     s0 = dr.stats()
     st0 = dr.renderer.stage_stats()
@@ -256,157 +412,110 @@ def bench_ours(args):
     ev0.record(dr.stream)
     for _ in range(args.steps):
         dr.clear()
-        dr.render(total_spp)
+        dr.render(spp)
+        dr.checkpoint()
     ev1.record(dr.stream)
     torch.cuda.synchronize()
     barrier()
     clocks = sampler.finish()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     s1 = dr.stats()
     st1 = dr.renderer.stage_stats()
-    samples_total = W * H * total_spp * args.steps
+    samples_total = W * H * spp * args.steps
     value = samples_total / ms_total / 1e3
-    launches = int(s1["kernel_launches"] - s0["kernel_launches"])
-    rays = int(s1["rays"] - s0["rays"])
-    frame = dr.frame(total_spp)
+    launches = int(sum_over_ranks(float(s1["kernel_launches"] - s0["kernel_launches"])))
+    rays = int(sum_over_ranks(float(s1["rays"] - s0["rays"])))
+    frame = dr.frame(spp)
     mean_radiance = [float(x) for x in frame.mean(axis=(0, 1))] if frame is not None else None
 
-    # ---- roofline of the dominant kernel (rank 0): live CUDA-event time per (kernel, depth) over the timed region,
-    #      algorithmic bytes from an instrumented pass of the same rays (C cells visited, T triangle tests)
-    roofline = None
-    stages = None
+    roofline = stages = None
     if rank == 0:
-        kinds = A.KERNEL_KINDS
-        d_ms = {k: [b - a for a, b in zip(st0["ms"][k], st1["ms"][k])] for k in kinds}
-        d_launch = {k: [b - a for a, b in zip(st0["launches"][k], st1["launches"][k])] for k in kinds}
-        d_rays = [b - a for a, b in zip(st0["rays"], st1["rays"])]
-        d_grid = [b - a for a, b in zip(st0["grid_rays"], st1["grid_rays"])]
-        d_shtri = [b - a for a, b in zip(st0["shaded_triangles"], st1["shaded_triangles"])]
-        counted = A.Renderer(scene, A.Settings(settings.camera_settings, 4, (32, 32), args.bounces),
-                             A.GpuOptions(device=local, seed=args.seed, flags=A.FLAG_COUNT_WORK, batch_spp=4))
-        counted.render(0, 4)
-        cs = counted.stage_stats()
-        counted.close()
-        total_ms = sum(sum(v) for v in d_ms.values())
-        stages, per_kernel = [], {}
-        kernel_bytes, survive, kernel_flops, ref_flops_min = {}, {}, {}, {}
-        for d in range(0, A.STAGE_SLOTS):
-            for k in kinds:
-                if d_launch[k][d] == 0:
-                    continue
-                C_ = T_ = None
-                if k == "accumulate":
-                    # reads 24 B per path, reads + writes 24 B per pixel per batch
-                    units, per_unit = samples_total / world, 24.0 + 48.0 * W * H * d_launch[k][d] / max(samples_total / world, 1)
-                elif k == "setup":
-                    # ray in (48 B; depth 1 generates it and writes it instead) + hit record out (16 B) + a 128-B traversal record per grid ray
-                    units = d_rays[d]
-                    per_unit = 48.0 + 16.0 + 128.0 * d_grid[d] / max(d_rays[d], 1)
-                elif k == "traverse":
-                    # B(ray) = 64 + 8 C + 76 T  (48-B ray in, 16-B hit out, 8 B per visited cell, 4 + 72 B per triangle test)
-                    g_ = max(cs["grid_rays"][d], 1)
-                    C_, T_ = cs["cells"][d] / g_, cs["triangle_tests"][d] / g_
-                    units, per_unit = d_grid[d], 64.0 + 8.0 * C_ + 76.0 * T_
-                    # what THIS kernel has to move for the same decisions: 128-B record + 16-B hit, a 4-B occupancy word per cell, an 8-B record
-                    # per occupied cell, a 16-B bounding sphere + 4-B triangle index per candidate, the 96-B positions per candidate not proven a miss
-                    kernel_bytes[d] = (144.0 + 4.0 * C_ + 8.0 * cs["occupied_cells"][d] / g_ + 20.0 * T_ + 96.0 * cs["evaluated_tests"][d] / g_) * d_grid[d]
-                    survive[d] = cs["evaluated_tests"][d] / max(cs["triangle_tests"][d], 1)
-                    # f64 add/sub/mul/div this kernel executes per grid ray: 1 per cell step (t_max += t_delta), 19 per bounding-sphere
-                    # pre-test, and the counted exits (20 / 30 / 46 / 52) of the Triangle::intersects calls it evaluates; the reference
-                    # runs Triangle::intersects on all T candidates (>= 20 each for the ones proven misses here)
-                    fl_eval = cs["evaluated_test_flops"][d] / g_
-                    kernel_flops[d] = (C_ + 19.0 * T_ + fl_eval) * d_grid[d]
-                    ref_flops_min[d] = (C_ + 20.0 * (T_ - cs["evaluated_tests"][d] / g_) + fl_eval) * d_grid[d]
-                else:
-                    # shade: ray + throughput + id + hit in (92 B), next ray out (76 B) or radiance out (24 B); +144 B (positions, normals) per shaded triangle
-                    units = d_rays[d]
-                    cont = d_rays[d + 1] if d + 1 < A.STAGE_SLOTS and d < args.bounces else 0
-                    per_unit = 92.0 + (76.0 * cont + 24.0 * (d_rays[d] - cont) + 144.0 * d_shtri[d]) / max(d_rays[d], 1)
-                bytes_total = per_unit * units
-                ms_ = d_ms[k][d]
-                stages.append({"kernel": "k_" + k, "depth": d, "ms": ms_, "launches": d_launch[k][d], "units": units,
-                               "alg_bytes_per_unit": per_unit, "cells_per_ray": C_, "tests_per_ray": T_,
-                               "achieved_gbs": bytes_total / (ms_ * 1e-3) / 1e9 if ms_ > 0 else None, "share": ms_ / max(total_ms, 1e-9)})
-                pk = per_kernel.setdefault(k, {"ms": 0.0, "launches": 0, "bytes": 0.0, "units": 0})
-                pk["ms"] += ms_; pk["launches"] += d_launch[k][d]; pk["bytes"] += bytes_total; pk["units"] += units
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:  # noqa: BLE001
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        top = max(per_kernel, key=lambda k: per_kernel[k]["ms"])
-        pk = per_kernel[top]
-        ach = pk["bytes"] / (pk["ms"] * 1e-3) / 1e9 if pk["ms"] > 0 else 0.0
-        fp64 = None
-        if top == "traverse":
-            fp64_peak = A.measure_fp64_rate(local)
-            ach_ops = sum(kernel_flops.values()) / (pk["ms"] * 1e-3) / 1e9
-            fp64 = {"peak_gops": fp64_peak, "peak_source": "measured live: independent DADD/DMUL stream, no FMA (the library is compiled -fmad=false "
-                                                           "to replay the reference's unfused f64 arithmetic), rm_measure_fp64_rate",
-                    "kernel_ops_per_unit": sum(kernel_flops.values()) / max(pk["units"], 1), "achieved_gops": ach_ops, "frac": ach_ops / fp64_peak,
-                    "reference_algorithm_ops_per_unit_min": sum(ref_flops_min.values()) / max(pk["units"], 1),
-                    "what": "f64 add/sub/mul/div per grid ray executed by k_traverse (C + 19 T + counted Triangle::intersects exits), against "
-                            "the device's no-FMA f64 rate; compares, selects, integer and address work are not counted"}
-        roofline = {"bound": "hbm", "kernel": "k_" + top, "fp64": fp64, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": (NCU_TRAFFIC_PER_UNIT["k_" + top] * pk["units"] / max(pk["launches"], 1)) if "k_" + top in NCU_TRAFFIC_PER_UNIT else None, "peak_source": peak_src,
-                    "alg_bytes_per_launch": pk["bytes"] / max(pk["launches"], 1), "alg_bytes_per_unit": pk["bytes"] / max(pk["units"], 1),
-                    "unit_name": "grid ray" if top == "traverse" else ("path" if top == "accumulate" else "ray"),
-                    "launch_ms_avg": pk["ms"] / max(pk["launches"], 1), "launches": pk["launches"], "share_of_step": pk["ms"] / max(total_ms, 1e-9),
-                    "per_kernel_share": {"k_" + k: v["ms"] / max(total_ms, 1e-9) for k, v in per_kernel.items()},
-                    "kernel_model": ({"bytes_per_unit": sum(kernel_bytes.values()) / max(pk["units"], 1),
-                                      "achieved_gbs": sum(kernel_bytes.values()) / (pk["ms"] * 1e-3) / 1e9,
-                                      "frac_of_hbm_peak": sum(kernel_bytes.values()) / (pk["ms"] * 1e-3) / 1e9 / peak,
-                                      "tests_evaluated_fraction": sum(survive.values()) / max(len(survive), 1),
-                                      "what": "bytes this kernel's own algorithm moves per grid ray: 144 + 4 C + 8 C_occupied + 20 T + 96 T_evaluated "
-                                              "(the bounding-sphere pre-test proves most of the reference's T triangle tests to be misses without fetching them)"}
-                                     if top == "traverse" else None),
-                    "traffic_note": "ncu dram bytes per grid ray (360 B, depths 1-3 of a 16-spp batch) x grid rays per launch; far BELOW the algorithmic bytes because the "
-                                    "150 MB traversal set is L2-resident and every triangle is fetched by many rays (L2 hit 85-89 %)",
-                    "note": "achieved/frac use the REFERENCE algorithm's bytes (SURVEY 8d: 64 + 8 C + 76 T); the kernel makes the same decisions while "
-                            "fetching far less (kernel_model), so frac can exceed 1. f64 no-FMA traversal of an L2-resident grid: the binding limits "
-                            "are instruction issue (ncu: 66-71 % issue-active, FP64 pipe 22-24 %, LSU data pipe 48-58 %) and L2 latency, not HBM "
-                            "(4-7 % of peak); see DESIGN.md section 6 and profiles/"}
+        roofline, stages = roofline_record(A, args, scene, settings, local, world, st0, st1, int(s1["samples"] - s0["samples"]), clocks)
     dr.close()
     del dr
 
-    # ---- end to end through the reference-facing call: render_tiled(scene, settings) -> await(), host buffers:
-    #      scene flatten + H2D inside, D2H of the f64 accumulator + tile slicing + averaging inside
-    e2e = None
+    # ---- BASELINE configs[2] and configs[4] at this N (scene resident, exchange inside, wall clock around barriers, max over ranks)
+    other = None
+    if not args.no_extras:
+        other = {}
+        sp = A.Scene.from_fixture(F.reflective_spheres())
+        c3 = A.Settings(A.CameraSettings.from_fixture(F.camera(1920, 1080, focal_length=2.5, aperture_radius=0.5)), args.c3_spp, (32, 32), 5)
+        d3 = D.DistributedRenderer(sp, c3, device=local, seed=args.seed, partition=A.PARTITION_TILES, precision=precision)
+        d3.render(min(50, args.c3_spp)); d3.sums()                # warm-up
+        barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
+        d3.clear(); d3.render(args.c3_spp); f3 = d3.frame(args.c3_spp)
+        torch.cuda.synchronize(); barrier()
+        sec = max_over_ranks(time.perf_counter() - t0)
+        other["c3_reflective_spheres_dof_1920x1080_tiles"] = {
+            "spp": args.c3_spp, "seconds": sec, "msamples_per_s": 1920 * 1080 * args.c3_spp / sec / 1e6, "partition": f"tiles round-robin over {world} GPU(s)",
+            "mean_radiance": None if f3 is None else float(f3.mean())}
+        d3.close()
+        del d3
+        spi5 = max(1, args.c5_spp // 16)                           # 16 checkpoints (256 at the full 4096 spp)
+        c5 = A.Settings(A.CameraSettings.from_fixture(F.camera(3840, 2160)), args.c5_spp, (32, 32), 5, samples_per_iteration=spi5)
+        d5 = D.DistributedRenderer(scene, c5, device=local, seed=args.seed, precision=precision)
+        d5.render(min(8, args.c5_spp)); d5.sums()                 # warm-up
+        barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
+        f5 = d5.render_progressive(None)                          # 16 checkpoints: copy + ncclReduce each, D2H of the final frame
+        torch.cuda.synchronize(); barrier()
+        sec = max_over_ranks(time.perf_counter() - t0)
+        other["c5_gold_dragon_3840x2160_progressive"] = {
+            "spp": args.c5_spp, "samples_per_iteration": spi5, "seconds": sec, "msamples_per_s": 3840 * 2160 * args.c5_spp / sec / 1e6,
+            "checkpoints": (args.c5_spp + spi5 - 1) // spi5, "partition": f"sample-split over {world} GPU(s)",
+            "mean_radiance": None if f5 is None else float(f5.mean())}
+        d5.close()
+        del d5, f5
+
+    # ---- end to end through the reference-facing call with host buffers: render_tiled(scene, settings).await() — scene flatten +
+    #      H2D inside, D2H of the f64 frame + tile slicing + averaging inside.  N > 1: (1) one process per GPU (torchrun), every
+    #      rank creates its renderer (scene upload), renders its share, exchange, frame on rank 0's host; (2) THE C-ABI call with
+    #      device_count = N from rank 0's process alone (the other ranks hand their cached device memory back and wait on the host).
+    e2e = e2e_torchrun = None
     if not args.no_e2e:
         e2e_steps = max(1, args.steps)
-        times, h2d, d2h = [], 0, W * H * 24
-        for i in range(1 + e2e_steps):
-            barrier()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            if world == 1:
-                task = A.render_tiled(scene, settings, A.GpuOptions(device=local, seed=args.seed + i))
-                out = task.await_()
-                stt = task.stats()
-                del task
-            else:
-                dre = D.DistributedRenderer(scene, settings, device=local, seed=args.seed + i)
-                dre.render(total_spp)
-                out = dre.frame(total_spp)
+        d2h = W * H * 24
+        if world > 1:
+            times, h2d = [], 0
+            for i in range(1 + e2e_steps):
+                barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
+                dre = D.DistributedRenderer(scene, settings, device=local, seed=args.seed + i, precision=precision)
+                dre.render(spp)
+                out = dre.frame(spp)
                 stt = dre.stats()
                 dre.close()
-            torch.cuda.synchronize()
-            barrier()
-            dt = time.perf_counter() - t0
-            h2d = int(stt["upload_bytes"])
-            if i > 0:
-                times.append(dt)
-        tt = torch.tensor([sum(times)], dtype=torch.float64, device=f"cuda:{local}")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": W * H * total_spp * e2e_steps / float(tt.item()) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": 1e3 * float(tt.item()) / e2e_steps,
-               "call": "render_tiled(scene, settings).await()" if world == 1 else "DistributedRenderer(create+render+reduce+frame)"}
+                torch.cuda.synchronize(); barrier()
+                if i > 0:
+                    times.append(time.perf_counter() - t0)
+                h2d = int(stt["upload_bytes"])
+            tt = max_over_ranks(sum(times))
+            e2e_torchrun = {"value": W * H * spp * e2e_steps / tt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(sum_over_ranks(float(h2d))),
+                            "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": 1e3 * tt / e2e_steps,
+                            "call": "per rank: DistributedRenderer(scene upload) + render(share) + ncclReduce + frame() on rank 0"}
+            A.release_cached_memory()
+        host_barrier()
+        if rank == 0:
+            times, h2d = [], 0
+            opts = dict(seed=args.seed, precision=precision)
+            if world > 1:
+                opts["device_list"] = list(range(world))
+            else:
+                opts["device"] = local
+            for i in range(1 + e2e_steps):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                task = A.render_tiled(scene, settings, A.GpuOptions(**dict(opts, seed=args.seed + i)))
+                out = task.await_()
+                dt = time.perf_counter() - t0
+                stt = task.stats()
+                del task
+                h2d = int(stt["upload_bytes"])
+                if i > 0:
+                    times.append(dt)
+            e2e = {"value": W * H * spp * e2e_steps / sum(times) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": 1e3 * sum(times) / e2e_steps,
+                   "call": "render_tiled(scene, settings).await()" + (f" with rm_gpu_options.device_count = {world} (one process drives all GPUs through the C ABI)" if world > 1 else ""),
+                   "mean_radiance": float(out.mean())}
+        host_barrier()
 
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample (rank 0, N=1 only)
     cpu = None
@@ -422,14 +531,12 @@ def bench_ours(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{label} {W}x{H}, {spp} spp per GPU ({total_spp} total), {args.bounces} bounces", "scene": args.scene,
-                       "spp_per_gpu": spp, "bounces": args.bounces, "tile": [32, 32], "parallelism": f"sample-split x{world} + ncclReduce(sum)",
-                       "l2": "inputs exceed L2 (scene ~250 MB + ~10 GB of wavefront queues per 16-spp batch); no explicit flush",
-                       "mesh": "stand-in" if args.scene == "gold_dragon" else "analytic"},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "mrays_per_s": rays * world / ms_total / 1e3 if world == 1 else None, "rays_per_path": rays / max(samples_total / world, 1),
+            "ms_per_step": ms_total / max(args.steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64" if args.precision == "f64" else "f64 intersection + f32 shading", "data": "synthetic",
+            "config": config_of(args, label),
+            "e2e": e2e, "e2e_torchrun": e2e_torchrun, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "other_configs": other,
+            "mrays_per_s": rays / ms_total / 1e3, "rays_per_path": rays / max(samples_total, 1),
             "stages": stages, "host_grid_build_s": host_build_s, "mean_radiance": mean_radiance,
             "nonfinite_samples": int(s1["nonfinite_samples"]),
         }
@@ -441,7 +548,7 @@ def bench_ours(args):
 def main():
     args = parse_args()
     # stdout carries exactly ONE JSON line: anything libraries write to file descriptor 1 meanwhile (NCCL prints its version
-    # banner there) is sent to stderr, and the descriptor is restored for the final print
+    # banner and, with NCCL_DEBUG=INFO, its log there) is sent to stderr, and the descriptor is restored for the final print
     sys.stdout.flush()
     saved = os.dup(1)
     os.dup2(2, 1)

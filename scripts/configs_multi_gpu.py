@@ -17,8 +17,6 @@ from raymond_b200 import api as A, distributed as D, fixtures as F
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 if world > 1:
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
-        os.environ["NCCL_DEBUG"] = "WARN"
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
 which = sys.argv[1:] or ["target", "C3", "C5"]
 
@@ -85,21 +83,10 @@ if "C5" in which:
 
     def run():
         dr = D.DistributedRenderer(dragon, st, device=local, seed=1)
-        # progressive: every `spi` samples the running sums of all ranks are combined on rank 0 (a checkpoint a viewer could
-        # show); each rank keeps accumulating its own sums, so the exchange goes through a scratch copy
-        scratch = torch.empty_like(dr.accum)
-        done = 0
-        while done < spp:
-            n = min(spi, spp - done)
-            first, count, stride = D.sample_share(n, rank, world)
-            if count:
-                dr.renderer.render(done + first, count, stride)
-            with torch.cuda.stream(dr.stream):
-                scratch.copy_(dr.accum)
-                D.reduce_sums(scratch, 0)
-            done += n
-        dr.synchronize()
-        mean = float((scratch / spp).mean()) if rank == 0 else None
+        # progressive (src/trace.rs:207-219): every `spi` samples a copy of every rank's running sums is reduced onto rank 0 (a
+        # checkpoint a viewer could show) while the ranks keep accumulating; the final frame is read back on rank 0
+        frame = dr.render_progressive(None)
+        mean = float(frame.mean()) if frame is not None else None
         dr.close()
         return mean
     t, mean = timed(run, 1)
