@@ -212,6 +212,9 @@ typedef enum rm_precision {
 #define RM_FLAG_KEEP_NONFINITE 1u  /* accumulate NaN/Inf samples like the reference instead of dropping+counting them */
 #define RM_FLAG_STAGE_TIMING 2u    /* bracket every kernel launch with CUDA events; totals per wavefront stage in rm_stage_stats */
 #define RM_FLAG_COUNT_WORK 4u      /* instrumented kernels: count grid cells visited and triangle tests per stage (slower) */
+#define RM_FLAG_NO_RAY_BINNING 8u  /* tuning: traverse the bounced rays in queue order instead of binned by (start cell, direction octant) */
+#define RM_FLAG_FUSE_SETUP 16u     /* tuning: force the fused shade + next-depth set-up kernel (default: only for scenes without a grid) */
+#define RM_FLAG_SPLIT_SETUP 32u    /* tuning: force separate shade and set-up kernels */
 
 /* GPU-side knobs that have no counterpart in the reference. Zero-initialise
  * for defaults (device 0, one rank, library-owned stream and buffers). */
@@ -335,12 +338,13 @@ int rm_renderer_stats(rm_renderer* r, rm_stats* out);
 /* Per-stage breakdown of the wavefront.  Slot d (1 <= d < RM_STAGE_SLOTS) is the stage that traces
  * and shades the rays of depth d (deeper stages share the last slot).  A stage is three kernels —
  * kind 0 set-up (ray generation / analytic objects / grid entry), kind 1 grid traversal, kind 2
- * shading — and kind 3, slot 0 is the accumulator kernel.  `ms` / `launches` need
+ * shading (fused with the next depth's set-up where the library fuses them) — kind 3, slot 0 is the accumulator kernel,
+ * and kind 4 the ray-binning kernels that order depth d's traversal records.  `ms` / `launches` need
  * RM_FLAG_STAGE_TIMING; `cells` / `triangle_tests` need RM_FLAG_COUNT_WORK; the rest is always
  * counted.  cells = C and triangle_tests = T of the algorithmic bytes-per-ray model
  * (64 + 8 C + 76 T, + 72 per shaded triangle hit). */
 #define RM_STAGE_SLOTS 16
-#define RM_KERNEL_KINDS 4
+#define RM_KERNEL_KINDS 5
 typedef struct rm_stage_stats {
     double ms[RM_KERNEL_KINDS][RM_STAGE_SLOTS];
     uint64_t launches[RM_KERNEL_KINDS][RM_STAGE_SLOTS];

@@ -50,6 +50,9 @@ PARTITION_TILES = 1
 FLAG_KEEP_NONFINITE = 1
 FLAG_STAGE_TIMING = 2
 FLAG_COUNT_WORK = 4
+FLAG_NO_RAY_BINNING = 8
+FLAG_FUSE_SETUP = 16
+FLAG_SPLIT_SETUP = 32
 PRECISION_F64 = 0
 PRECISION_F32_SHADING = 1
 STAGE_SLOTS = 16
@@ -105,11 +108,11 @@ class StatsC(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
-KERNEL_KINDS = ("setup", "traverse", "shade", "accumulate")
+KERNEL_KINDS = ("setup", "traverse", "shade", "accumulate", "bin")
 
 
 class StageStatsC(C.Structure):
-    _fields_ = [("ms", (C.c_double * STAGE_SLOTS) * 4), ("launches", (C.c_uint64 * STAGE_SLOTS) * 4)] + \
+    _fields_ = [("ms", (C.c_double * STAGE_SLOTS) * len(KERNEL_KINDS)), ("launches", (C.c_uint64 * STAGE_SLOTS) * len(KERNEL_KINDS))] + \
                [(n, C.c_uint64 * STAGE_SLOTS) for n in ("rays", "grid_rays", "cells", "triangle_tests", "shaded_triangles", "evaluated_tests", "occupied_cells", "evaluated_test_flops")]
 
     def as_dict(self) -> dict:

@@ -113,7 +113,8 @@ void* pinned_acquire(size_t bytes) {
         // drop cached blocks that are too small before pinning a bigger one
         for (PinnedBlock& f : g_pin_free) cudaFreeHost(f.p);
         g_pin_free.clear();
-        if (cudaMallocHost(&b.p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        // portable + mapped: every device of the process can DMA from it and write to it from a kernel (the accumulator exchange does)
+        if (cudaHostAlloc(&b.p, bytes, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return nullptr; }
         b.bytes = bytes;
     }
     g_pin_busy.push_back(b);
@@ -394,13 +395,13 @@ struct NoHook : LaunchHook {
 // order) `buf.hit` holds the closest hit of every ray.  `trav_count` / `cursor` are zero on entry and
 // re-zeroed between grid passes.
 template <int SRC>
-static int launch_intersect(rm_device_scene* ds, const RenderParams& rp, SetupArgs sa, const IntersectBuffers& buf, unsigned* trav_count,
+static int launch_intersect(rm_device_scene* ds, const RenderParams& rp, SetupArgs sa, const HitArrays& hit, double* trav, unsigned* trav_count,
                             unsigned* cursor, unsigned n_upper, unsigned depth, bool count_work, DevTotals* totals, cudaStream_t stream,
                             LaunchHook& hook) {
     const unsigned setup_grid = std::max<unsigned>(1u, std::min<unsigned>((n_upper + kBlock - 1) / kBlock, (unsigned)ds->sms * 16u));
     const unsigned trav_grid = (unsigned)(ds->sms * ds->traverse_blocks_per_sm);
-    sa.hit = buf.hit;
-    sa.trav = buf.trav;
+    sa.hit = hit;
+    sa.trav = trav;
     sa.trav_count = trav_count;
     const size_t n_grid_objects = ds->grid_objects.size();
     for (size_t pass = 0; pass < std::max<size_t>(n_grid_objects, 1); pass++) {
@@ -418,7 +419,7 @@ static int launch_intersect(rm_device_scene* ds, const RenderParams& rp, SetupAr
         hook.end(0);
         if (gobj >= 0) {
             TraverseArgs ta{};
-            ta.trav = buf.trav; ta.n_ptr = trav_count; ta.cursor = cursor; ta.hit = buf.hit;
+            ta.trav = trav; ta.n_ptr = trav_count; ta.cursor = cursor; ta.hit = hit;
             ta.grid_object = gobj; ta.depth = depth; ta.totals = totals;
             const DevGrid& g = ds->scene.grid[ds->scene.obj[gobj].grid];
             hook.begin(1);
@@ -462,6 +463,7 @@ struct rm_renderer {
     struct StageEvent { cudaEvent_t a, b; unsigned kind, slot; };
     std::vector<StageEvent> stage_pending;
     std::vector<cudaEvent_t> event_pool;
+    cudaEvent_t ev_rendered = nullptr, ev_reduced = nullptr;      // accumulator exchange between the renderers of one task
     double stage_ms[RM_KERNEL_KINDS][RM_STAGE_SLOTS] = {};
     uint64_t stage_launches[RM_KERNEL_KINDS][RM_STAGE_SLOTS] = {};
 
@@ -471,6 +473,8 @@ struct rm_renderer {
         for (auto& p : pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
         for (auto& e : stage_pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
         for (auto& e : event_pool) cudaEventDestroy(e);
+        if (ev_rendered) cudaEventDestroy(ev_rendered);
+        if (ev_reduced) cudaEventDestroy(ev_reduced);
         dev_free(queue_mem); dev_free(id_mem); dev_free(pixel_map); dev_free(rp.contrib); dev_free(counters); dev_free(totals);
         isect.release();
         if (owns_accum) dev_free(accum);
@@ -510,7 +514,7 @@ static int renderer_init(rm_renderer* r) {
     if (s.bounce_limit > 1u << 20) return fail(RM_ERR_UNSUPPORTED, "bounce_limit too large");
     if (r->opt.world_size > 1 && (r->opt.rank < 0 || r->opt.rank >= r->opt.world_size)) return fail(RM_ERR_INVALID_ARGUMENT, "rank outside world_size");
     RM_CUDA(cudaSetDevice(r->device));
-    r->sms = r->ds->sms;
+    r->sms = sm_count(r->device);
     if (r->opt.stream) r->stream = (cudaStream_t)r->opt.stream;
     else { RM_CUDA(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking)); r->owns_stream = true; }
 
@@ -544,6 +548,7 @@ static int renderer_init(rm_renderer* r) {
         r->q[b].id = r->id_mem + (size_t)b * cap;
     }
     if (int st = r->isect.alloc(cap)) return st;
+    if (r->opt.precision != RM_PRECISION_F64 && r->opt.precision != RM_PRECISION_F32_SHADING) return fail(RM_ERR_INVALID_ARGUMENT, "unknown rm_precision");
     RenderParams& rp = r->rp;
     rp.cam = make_camera(s.camera_settings);
     rp.seed = r->opt.seed;
@@ -594,7 +599,8 @@ struct StageHook : LaunchHook {
     }
 };
 
-static int renderer_batch(rm_renderer* r, unsigned first_sample, unsigned n_samples, unsigned stride) {
+template <int PREC>
+static int renderer_batch_t(rm_renderer* r, unsigned first_sample, unsigned n_samples, unsigned stride) {
     RenderParams rp = r->rp;
     rp.first_sample = first_sample;
     rp.sample_stride = stride;
@@ -614,20 +620,20 @@ static int renderer_batch(rm_renderer* r, unsigned first_sample, unsigned n_samp
         int st;
         if (depth == 1) {
             sa.n_ptr = nullptr; sa.n_direct = n_paths;
-            st = launch_intersect<SRC_CAMERA>(r->ds, rp, sa, r->isect, &rp.cnt.trav[depth], &rp.cnt.cursor[depth], n_paths, depth, count, r->totals,
-                                              r->stream, hook);
+            st = launch_intersect<SRC_CAMERA>(r->ds, rp, sa, r->isect.hit, r->isect.trav, &rp.cnt.trav[depth], &rp.cnt.cursor[depth], n_paths, depth, count,
+                                              r->totals, r->stream, hook);
         } else {
             sa.n_ptr = &rp.cnt.rays[depth - 1]; sa.n_direct = 0;
-            st = launch_intersect<SRC_QUEUE>(r->ds, rp, sa, r->isect, &rp.cnt.trav[depth], &rp.cnt.cursor[depth], persistent_grid * kBlock, depth, count,
-                                             r->totals, r->stream, hook);
+            st = launch_intersect<SRC_QUEUE>(r->ds, rp, sa, r->isect.hit, r->isect.trav, &rp.cnt.trav[depth], &rp.cnt.cursor[depth], persistent_grid * kBlock,
+                                             depth, count, r->totals, r->stream, hook);
         }
         if (st != RM_OK) return st;
         hook.begin(2);
         if (depth == 1) {
             const unsigned grid = std::min<unsigned>((n_paths + kBlock - 1) / kBlock, persistent_grid * 4u);
-            k_shade<true><<<grid, kBlock, 0, r->stream>>>(r->ds->scene, rp, qin, qout, r->isect.hit, depth, n_paths);
+            k_shade<true, PREC><<<grid, kBlock, 0, r->stream>>>(r->ds->scene, rp, qin, qout, r->isect.hit, depth, n_paths);
         } else {
-            k_shade<false><<<persistent_grid, kBlock, 0, r->stream>>>(r->ds->scene, rp, qin, qout, r->isect.hit, depth, 0u);
+            k_shade<false, PREC><<<persistent_grid, kBlock, 0, r->stream>>>(r->ds->scene, rp, qin, qout, r->isect.hit, depth, 0u);
         }
         hook.end(2);
     }
@@ -639,6 +645,11 @@ static int renderer_batch(rm_renderer* r, unsigned first_sample, unsigned n_samp
     }
     RM_CUDA(cudaGetLastError());
     return RM_OK;
+}
+
+static int renderer_batch(rm_renderer* r, unsigned first_sample, unsigned n_samples, unsigned stride) {
+    if (r->opt.precision == RM_PRECISION_F32_SHADING) return renderer_batch_t<RM_PRECISION_F32_SHADING>(r, first_sample, n_samples, stride);
+    return renderer_batch_t<RM_PRECISION_F64>(r, first_sample, n_samples, stride);
 }
 
 static void harvest_events(rm_renderer* r) {
@@ -666,8 +677,88 @@ __global__ void __launch_bounds__(256) k_add(double* __restrict__ total, const d
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) total[i] += part[i];
 }
 
-int reduce_accumulators_to_host(rm_renderer* const* rs, int count, rm_vec3* out) {
+// The accumulator exchange of a multi-device task as ONE pass: elements [begin, end) of the frame summed over all the
+// devices' accumulators (read in place over NVLink peer mappings, in device order — the association of a sequential
+// "total += part" chain, so the frame does not depend on which device sums which slice) and written straight into the
+// pinned host frame the tile messages are sliced from.  Every device runs this on its own slice: reduce-scatter over
+// peer memory + the D2H of the result over that device's own PCIe link, no staging copy, no gather onto one device.
+constexpr int kMaxShares = 64;
+struct SharePointers {
+    const double* acc[kMaxShares];
+    int count;
+};
+__global__ void __launch_bounds__(256) k_reduce_slice(const __grid_constant__ SharePointers p, double* __restrict__ out, size_t begin, size_t end) {
+    for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (size_t)gridDim.x * blockDim.x) {
+        double s = p.acc[0][i];
+        for (int j = 1; j < p.count; j++) s += p.acc[j][i];
+        out[i] = s;
+    }
+}
+
+static int reduce_gather_to_host(rm_renderer* const* rs, int count, rm_vec3* out);
+
+int reduce_accumulators_to_host(rm_renderer* const* rs, int count, rm_vec3* out, bool out_is_pinned) {
     if (count <= 0 || !rs || !out) return fail(RM_ERR_INVALID_ARGUMENT, "reduce_accumulators_to_host: bad argument");
+    rm_renderer* r0 = rs[0];
+    const size_t n = r0->settings.camera_settings.backbuffer_width * r0->settings.camera_settings.backbuffer_height * 3;
+    if (count == 1) {
+        RM_CUDA(cudaSetDevice(r0->device));
+        RM_CUDA(cudaMemcpyAsync(out, r0->accum, n * sizeof(double), cudaMemcpyDeviceToHost, r0->stream));
+        RM_CUDA(cudaStreamSynchronize(r0->stream));
+        return RM_OK;
+    }
+    if (!out_is_pinned || count > kMaxShares) return reduce_gather_to_host(rs, count, out);
+    for (int g = 0; g < count; g++)
+        for (int j = 0; j < count; j++) {
+            int can = 1;
+            if (rs[g]->device != rs[j]->device && (cudaDeviceCanAccessPeer(&can, rs[g]->device, rs[j]->device) != cudaSuccess || !can)) {
+                cudaGetLastError();
+                return reduce_gather_to_host(rs, count, out);       // no peer mapping between these two devices: staged copies
+            }
+        }
+    // the frame as the devices see it (the same address under unified addressing)
+    double* out_dev = nullptr;
+    RM_CUDA(cudaSetDevice(r0->device));
+    if (cudaHostGetDevicePointer((void**)&out_dev, (void*)out, 0) != cudaSuccess) { cudaGetLastError(); return reduce_gather_to_host(rs, count, out); }
+    SharePointers p{};
+    p.count = count;
+    for (int g = 0; g < count; g++) p.acc[g] = rs[g]->accum;
+    for (int g = 0; g < count; g++) {
+        RM_CUDA(cudaSetDevice(rs[g]->device));
+        if (!rs[g]->ev_rendered) RM_CUDA(cudaEventCreateWithFlags(&rs[g]->ev_rendered, cudaEventDisableTiming));
+        if (!rs[g]->ev_reduced) RM_CUDA(cudaEventCreateWithFlags(&rs[g]->ev_reduced, cudaEventDisableTiming));
+        RM_CUDA(cudaEventRecord(rs[g]->ev_rendered, rs[g]->stream));
+    }
+    for (int g = 0; g < count; g++) {
+        rm_renderer* r = rs[g];
+        RM_CUDA(cudaSetDevice(r->device));
+        for (int j = 0; j < count; j++)
+            if (j != g) RM_CUDA(cudaStreamWaitEvent(r->stream, rs[j]->ev_rendered, 0));      // everything the peers rendered is complete
+        const size_t begin = (n * (size_t)g / (size_t)count) & ~(size_t)31, end = g + 1 == count ? n : (n * (size_t)(g + 1) / (size_t)count) & ~(size_t)31;
+        if (end > begin) {
+            const unsigned blocks = (unsigned)std::min<size_t>((end - begin + 255) / 256, (size_t)r->sms * 8);
+            k_reduce_slice<<<blocks, 256, 0, r->stream>>>(p, out_dev, begin, end);
+            r->launches++;
+        }
+        RM_CUDA(cudaGetLastError());
+        RM_CUDA(cudaEventRecord(r->ev_reduced, r->stream));
+    }
+    // no device goes on accumulating before every peer has read its sums (the exchange is non-destructive: rendering continues)
+    for (int g = 0; g < count; g++) {
+        RM_CUDA(cudaSetDevice(rs[g]->device));
+        for (int j = 0; j < count; j++)
+            if (j != g) RM_CUDA(cudaStreamWaitEvent(rs[g]->stream, rs[j]->ev_reduced, 0));
+    }
+    for (int g = 0; g < count; g++) {
+        cudaError_t e = cudaEventSynchronize(rs[g]->ev_reduced);
+        if (e != cudaSuccess) return fail(RM_ERR_CUDA, std::string("accumulator exchange: ") + cudaGetErrorString(e));
+    }
+    return RM_OK;
+}
+
+// Fallback when the destination is pageable memory (pinning failed) or there are more shares than one kernel takes: sum onto
+// the first device with peer copies + an add kernel per peer, in renderer order, then one D2H copy.
+static int reduce_gather_to_host(rm_renderer* const* rs, int count, rm_vec3* out) {
     rm_renderer* r0 = rs[0];
     const size_t n = r0->settings.camera_settings.backbuffer_width * r0->settings.camera_settings.backbuffer_height * 3;
     for (int g = 1; g < count; g++) {            // everything the peers rendered must be complete before it is copied
@@ -675,18 +766,11 @@ int reduce_accumulators_to_host(rm_renderer* const* rs, int count, rm_vec3* out)
         RM_CUDA(cudaStreamSynchronize(rs[g]->stream));
     }
     RM_CUDA(cudaSetDevice(r0->device));
-    if (count == 1) {
-        RM_CUDA(cudaMemcpyAsync(out, r0->accum, n * sizeof(double), cudaMemcpyDeviceToHost, r0->stream));
-        RM_CUDA(cudaStreamSynchronize(r0->stream));
-        return RM_OK;
-    }
     double *total = nullptr, *part = nullptr;
     RM_CUDA(dev_malloc(&total, n * sizeof(double)));
     RM_CUDA(dev_malloc(&part, n * sizeof(double)));
     cudaError_t e = cudaMemcpyAsync(total, r0->accum, n * sizeof(double), cudaMemcpyDeviceToDevice, r0->stream);
     for (int g = 1; g < count && e == cudaSuccess; g++) {
-        cudaDeviceEnablePeerAccess(rs[g]->device, 0);        // NVLink P2P when available; the copy works either way
-        cudaGetLastError();
         e = cudaMemcpyPeerAsync(part, r0->device, rs[g]->accum, rs[g]->device, n * sizeof(double), r0->stream);
         if (e == cudaSuccess) {
             k_add<<<(unsigned)std::min<size_t>((n + 255) / 256, (size_t)r0->sms * 16), 256, 0, r0->stream>>>(total, part, n);
@@ -810,7 +894,8 @@ int rm_device_scene_intersect(rm_device_scene* ds, const rm_ray* rays, size_t co
     sa.n_ptr = nullptr;
     sa.n_direct = (unsigned)count;
     NoHook hook;
-    if (int st = launch_intersect<SRC_AOS>(ds, rp, sa, ds->query, ds->query_counters, ds->query_counters + 1, (unsigned)count, 1u, false, nullptr, stream, hook))
+    if (int st = launch_intersect<SRC_AOS>(ds, rp, sa, ds->query.hit, ds->query.trav, ds->query_counters, ds->query_counters + 1, (unsigned)count, 1u, false,
+                                           nullptr, stream, hook))
         return st;
     const size_t blocks = std::min<size_t>((count + kBlock - 1) / kBlock, (size_t)ds->sms * 32);
     k_export_hits<<<(unsigned)blocks, kBlock, 0, stream>>>(ds->query.hit, count, (long long*)obj, (unsigned long long*)sub, distance);
@@ -859,15 +944,42 @@ int rm_scene_intersect(const rm_scene* scene, int device, const rm_ray* rays, si
     return st;
 }
 
-rm_renderer* rm_renderer_create_on(rm_device_scene* ds, const rm_settings* settings, const rm_gpu_options* options) {
-    if (!ds || !settings) { fail(RM_ERR_INVALID_ARGUMENT, "rm_renderer_create_on: null argument"); return nullptr; }
+/* A renderer without a scene yet: stream, pixel map, wavefront queues, accumulator on options->device.  Lets the shares of a
+ * multi-device task set themselves up while the scene is still being uploaded / cloned. */
+rm_renderer* rm_renderer_create_unbound(const rm_settings* settings, const rm_gpu_options* options) {
+    if (!settings) { fail(RM_ERR_INVALID_ARGUMENT, "rm_renderer_create_unbound: null argument"); return nullptr; }
     rm_renderer* r = new rm_renderer();
-    r->ds = ds;
     r->settings = *settings;
     if (options) r->opt = *options;
-    r->opt.device = ds->device;
-    r->device = ds->device;
+    r->opt.device_list = nullptr;
+    r->device = r->opt.device;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || r->device < 0 || r->device >= count) {
+        fail(RM_ERR_CUDA, std::string("no usable CUDA device ") + std::to_string(r->device) + " (" + (e != cudaSuccess ? cudaGetErrorString(e) : "ordinal out of range") +
+                              "); this library has no CPU path");
+        delete r;
+        return nullptr;
+    }
     if (renderer_init(r) != RM_OK) { delete r; return nullptr; }
+    return r;
+}
+
+int rm_renderer_bind_scene(rm_renderer* r, rm_device_scene* ds, int owning) {
+    if (!r || !ds) return fail(RM_ERR_INVALID_ARGUMENT, "rm_renderer_bind_scene: null argument");
+    if (ds->device != r->device) return fail(RM_ERR_INVALID_ARGUMENT, "rm_renderer_bind_scene: the scene lives on another device");
+    r->ds = ds;
+    r->owns_scene = owning != 0;
+    return RM_OK;
+}
+
+rm_renderer* rm_renderer_create_on(rm_device_scene* ds, const rm_settings* settings, const rm_gpu_options* options) {
+    if (!ds || !settings) { fail(RM_ERR_INVALID_ARGUMENT, "rm_renderer_create_on: null argument"); return nullptr; }
+    rm_gpu_options o{};
+    if (options) o = *options;
+    o.device = ds->device;
+    rm_renderer* r = rm_renderer_create_unbound(settings, &o);
+    if (r) rm_renderer_bind_scene(r, ds, 0);
     return r;
 }
 
@@ -883,6 +995,7 @@ rm_renderer* rm_renderer_create(const rm_scene* scene, const rm_settings* settin
 
 int rm_renderer_render(rm_renderer* r, size_t first_sample, size_t count, size_t stride) {
     if (!r) return fail(RM_ERR_INVALID_ARGUMENT, "rm_renderer_render: null renderer");
+    if (!r->ds) return fail(RM_ERR_STATE, "rm_renderer_render: no scene bound to the renderer");
     if (stride == 0) stride = 1;
     if (first_sample + count * stride >= 0xffffffffull) return fail(RM_ERR_UNSUPPORTED, "sample index beyond 2^32");
     RM_CUDA(cudaSetDevice(r->device));
@@ -995,8 +1108,8 @@ int rm_renderer_stats(rm_renderer* r, rm_stats* out) {
     out->nonfinite_samples = t.nonfinite;
     out->kernel_launches = r->launches;
     out->device_ms = r->device_ms;
-    out->upload_ms = r->ds->upload_ms;
-    out->upload_bytes = r->ds->bytes + (uint64_t)r->rp.n_pixels * sizeof(unsigned);
+    out->upload_ms = r->ds ? r->ds->upload_ms : 0.0;
+    out->upload_bytes = (r->ds ? r->ds->bytes : 0) + (uint64_t)r->rp.n_pixels * sizeof(unsigned);
     return RM_OK;
 }
 

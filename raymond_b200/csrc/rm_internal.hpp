@@ -2,6 +2,9 @@
 #pragma once
 
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <condition_variable>
 #include <cstdint>
 #include <deque>
@@ -79,13 +82,25 @@ struct TileRect { size_t left, top, width, height; };
 std::vector<TileRect> tile_layout(size_t W, size_t H, size_t tw, size_t th);
 
 // Device memory from the cached stream-ordered pool (rm_device.cu); dev_alloc returns a cudaError_t value (0 = ok).
-// Sum of the accumulators of several renderers (one per device) into pinned host memory: peer copies onto the first
-// renderer's device + an add kernel per peer, in renderer order (rm_device.cu).  Synchronises every renderer's stream.
-int reduce_accumulators_to_host(rm_renderer* const* renderers, int count, rm_vec3* out_pinned);
+// Sum of the accumulators of several renderers (one per share of a task) into a host frame (rm_device.cu).  With a pinned
+// destination every device sums its slice of the frame from all peers' accumulators in place (peer reads over NVLink) and
+// writes it straight to the host; otherwise the sums are gathered onto the first device and copied.  Either way the sum
+// is taken in renderer order, the renderers' accumulators are left as they are, and on return the frame is complete.
+int reduce_accumulators_to_host(rm_renderer* const* renderers, int count, rm_vec3* out, bool out_is_pinned);
 // display transform kernel (rm_display.cu): sums / divisor -> tonemap -> 8-bit RGB, device pointers
 int tonemap_device(const double* sums_device, size_t n_pixels, double divisor, double exposure, double gamma, unsigned char* out_device, void* stream);
 int dev_alloc(void** p, size_t bytes);
 void dev_release(void* p);
+
+// RM_TRACE=1 in the environment: phase timings of rm_render_tiled / the render driver on stderr (host-path tuning)
+struct Trace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    Trace() : on(getenv("RM_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) const {
+        if (on) fprintf(stderr, "[rm_trace] %8.3f ms  %s\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), what);
+    }
+};
 
 }  // namespace rm
 
@@ -93,6 +108,8 @@ void dev_release(void* p);
 extern "C" {
 rm_device_scene* rm_device_scene_clone_to(const rm_device_scene* src, int device);
 rm_renderer* rm_renderer_create_owning(rm_device_scene* ds, const rm_settings* settings, const rm_gpu_options* options);
+rm_renderer* rm_renderer_create_unbound(const rm_settings* settings, const rm_gpu_options* options);
+int rm_renderer_bind_scene(rm_renderer* r, rm_device_scene* ds, int owning);
 rm_device_scene* rm_renderer_device_scene(rm_renderer* r);
 }
 

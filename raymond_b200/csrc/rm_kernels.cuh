@@ -14,6 +14,9 @@
 //   k_shade     one thread per ray: surface normal, material, lobe choice, BRDF weight, next ray or
 //               delivered radiance; survivors are compacted into the next stage's ray queue
 // followed once per batch by k_accumulate (the tile accumulator).
+// (Round 2 measured two variations of this pipeline and kept neither — profiles/r2_ab_fusion_binning_f32.log: k_shade fused with
+// the next depth's k_setup starves on instruction fetch, 4 000-5 000 SASS instructions, stall_no_instruction 6.4 per issue;
+// binning the bounced rays by start cell and direction octant before k_traverse buys 4 % of its time and costs as much.)
 //
 // Build with -fmad=false: rustc never contracts a*b+c, and every f64 add/mul/div/sqrt below is one
 // IEEE operation in the reference's order.  Citations are relative to the reference checkout.
@@ -464,27 +467,36 @@ __device__ __forceinline__ D3 triangle_normal(const DevGrid& g, unsigned ti, D3 
     return normalize((n2 * ba) + (n1 * bb) + (n0 * bc));
 }
 
-// One bounce of `trace` (src/trace.rs:232-320) in throughput form: the recursion multiplies the
-// child radiance by a weight known before recursing, so a path's value is (prod of weights) (*)
-// emission.  Returns true when the path continues with (o, d, T) updated; otherwise `result` is
-// the radiance the path delivers.
-__device__ __forceinline__ bool shade(const DevScene& sc, const RenderParams& rp, double hit_t, int hit_obj, unsigned hit_sub, unsigned pixel,
-                                      unsigned sample, unsigned depth, D3& o, D3& d, D3& T, D3& result, unsigned& shaded_tri) {
-    result = d3(0.0, 0.0, 0.0);
-    if (hit_obj < 0) return false;                                          // :242
-    const DevObject& ob = sc.obj[hit_obj];
-    const D3 frag = o + d * hit_t;                                          // :246
-    if (ob.mat == RM_MATERIAL_EMISSION) { result = mul(T, ld3(ob.color)); return false; }   // :250
-    if (depth >= rp.bounce_limit) return false;                             // the child call returns 0 (:235-237)
-    D3 normal;                                                              // :244
-    if (ob.geom == GEOM_PLANE) normal = ld3(ob.g + 3);
-    else if (ob.geom == GEOM_SPHERE) normal = normalize(frag - ld3(ob.g));
-    else { normal = triangle_normal(sc.grid[ob.grid], hit_sub, frag); shaded_tri++; }
+// ---- f32 helpers of the statistical scope (RM_PRECISION_F32_SHADING).  The TU is compiled with -fmad=false (the bit-exact
+// scope must not contract), so the FMAs here are written out.
+struct F3 { float x, y, z; };
+__device__ __forceinline__ F3 f3(float x, float y, float z) { F3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ F3 f3(D3 a) { return f3((float)a.x, (float)a.y, (float)a.z); }
+__device__ __forceinline__ F3 operator+(F3 a, F3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ F3 operator*(F3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float dotf(F3 a, F3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+__device__ __forceinline__ F3 normalizef(F3 a) { return a * rsqrtf(dotf(a, a)); }
+// a * s + b
+__device__ __forceinline__ F3 madf(F3 a, float s, F3 b) { return f3(fmaf(a.x, s, b.x), fmaf(a.y, s, b.y), fmaf(a.z, s, b.z)); }
+__device__ __forceinline__ float pow5f(float x) { const float x2 = x * x; return x2 * x2 * x; }
+// 23 bits -> (k + 0.5) * 2^-23: exactly representable, strictly inside (0, 1)
+__device__ __forceinline__ float u23(unsigned w) { return ((float)(w >> 9) + 0.5f) * (1.0f / 8388608.0f); }
+// sin / cos of an angle of any size the GGX lobe produces (theta = a sqrt(r / (1 - r)) <= ~4100 a with 23-bit uniforms): two-term
+// Cody-Waite reduction to [-pi, pi], then the hardware approximations (abs. error ~5e-7, far below the Monte-Carlo noise)
+__device__ __forceinline__ void sincos_reduced(float x, float& s, float& c) {
+    const float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(-k, 6.2831854820251465f, x);
+    r = fmaf(-k, -1.7484555314695172e-07f, r);
+    s = __sinf(r);
+    c = __cosf(r);
+}
 
-    const D3 color = ld3(ob.color);
-    const double rough = ob.rough;
-    const double metal = ob.mat == RM_MATERIAL_METAL ? 1.0 : 0.0;
-    const D3 view = normalize(ld3(rp.cam.pos) - frag);                      // :256 (always the camera position)
+// The lobe choice, direction sample and BRDF weight of one bounce (src/trace.rs:256-319) in f64 exactly as written: the
+// reference's operations in the reference's order.  normal / view are unit vectors; returns the next direction, the weight the
+// child radiance is multiplied by, and the ray offset along the normal.
+__device__ __forceinline__ void lobe_f64(const RenderParams& rp, D3 normal, D3 to_camera, D3 color, double rough, double metal, unsigned pixel, unsigned sample,
+                                         unsigned depth, D3& dir_out, D3& wgt, double& eps) {
+    const D3 view = normalize(to_camera);                                   // :256 (always towards the camera position)
     const D3 f0 = d3(0.04 + metal * (color.x - 0.04), 0.04 + metal * (color.y - 0.04), 0.04 + metal * (color.z - 0.04));
     unsigned w[4];
     philox(rp.seed, pixel, sample, depth, 0u, w);
@@ -499,7 +511,7 @@ __device__ __forceinline__ bool shade(const DevScene& sc, const RenderParams& rp
     const bool diffuse_lobe = r < prob_d;
     const double kTwoPi = 2.0 * 3.14159265358979323846;
     D3 axis;
-    double s_t, c_t, phi, eps;       // sin / cos of the polar angle, azimuth, ray offset
+    double s_t, c_t, phi;            // sin / cos of the polar angle, azimuth
     if (diffuse_lobe) {
         // cosine-weighted hemisphere: theta = acos(sqrt(r1)), pdf = sqrt(r1)      :396-406
         c_t = sqrt(ra); s_t = sqrt(1.0 - ra);
@@ -524,7 +536,6 @@ __device__ __forceinline__ bool shade(const DevScene& sc, const RenderParams& rp
     const D3 half = normalize(light + view);                                    // :276 / :308
     const double hv = dot(half, view);
     const D3 one = d3(1.0, 1.0, 1.0);
-    D3 wgt;
     if (diffuse_lobe) {
         const double cos_theta = fmax(ndl, 0.0);                                // :275
         const D3 fres = f0 + (one - f0) * pow5(1.0 - fmax(hv, 0.0));            // :277
@@ -545,6 +556,99 @@ __device__ __forceinline__ bool shade(const DevScene& sc, const RenderParams& rp
         const double pdf = (D * nh) / (4.0 * hv) + 0.0001;                      // :317
         wgt = (((nom / denom) * ndl) / (1.0 - prob_d)) / pdf;
     }
+    dir_out = dir;
+}
+
+// The same bounce with the statistical scope in f32 (RM_PRECISION_F32_SHADING): same formulas, same lobe probabilities, 23-bit
+// uniforms from one Philox call, FMAs, rsqrt normalisations.  The result agrees with lobe_f64 to ~1e-6 relative, i.e. far
+// inside the Monte-Carlo noise the image tolerance of SURVEY 8d is defined by; the direction is re-normalised in f64 so the
+// intersection code downstream still sees |d| = 1 to f64 accuracy.
+__device__ __forceinline__ void lobe_f32(const RenderParams& rp, D3 normal64, D3 to_camera, D3 color64, double rough64, double metal64, unsigned pixel,
+                                         unsigned sample, unsigned depth, D3& dir_out, D3& wgt_out, double& eps) {
+    const F3 normal = f3(normal64), view = normalizef(f3(to_camera)), color = f3(color64);
+    const float rough = (float)rough64, metal = (float)metal64;
+    const F3 f0 = f3(fmaf(metal, color.x - 0.04f, 0.04f), fmaf(metal, color.y - 0.04f, 0.04f), fmaf(metal, color.z - 0.04f, 0.04f));
+    unsigned w[4];
+    philox(rp.seed, pixel, sample, depth, 0u, w);
+    const float r = u23(w[0]), ra = u23(w[2]), rb = u23(w[1]);
+    const float prob_d = 0.5f - 0.5f * metal;
+    const bool diffuse_lobe = r < prob_d;
+    F3 axis;
+    float s_t, c_t, sp, cp;
+    if (diffuse_lobe) {
+        c_t = sqrtf(ra); s_t = sqrtf(1.0f - ra);
+        sincospif(2.0f * rb, &sp, &cp);
+        axis = normal;
+        eps = 0.00001;
+    } else {
+        axis = normalizef(madf(normal, 2.0f * dotf(view, normal), f3(-view.x, -view.y, -view.z)));
+        sincospif(2.0f * ra, &sp, &cp);
+        sincos_reduced((rough * rough) * sqrtf(__fdividef(rb, 1.0f - rb)), s_t, c_t);
+        eps = 0.0001;
+    }
+    // create_coordinate_system_of_n (:408-416) around the axis, then Matrix3::from_cols(t, axis, b) * (s cos, c, s sin)
+    const float sign = axis.z > 0.0f ? 1.0f : -1.0f;
+    const float a_ = -1.0f / (sign + axis.z);
+    const float bb = axis.x * axis.y * a_;
+    const F3 tg = f3(fmaf(sign * axis.x, axis.x * a_, 1.0f), sign * bb, -sign * axis.x);
+    const F3 bt = f3(bb, fmaf(axis.y, axis.y * a_, sign), -axis.y);
+    const F3 dir = normalizef(madf(bt, s_t * sp, madf(axis, c_t, tg * (s_t * cp))));
+    const float ndl = dotf(normal, dir);
+    const F3 half = normalizef(dir + view);
+    const float hv = dotf(half, view);
+    F3 wgt;
+    if (diffuse_lobe) {
+        const float cos_theta = fmaxf(ndl, 0.0f);
+        const float fr = pow5f(1.0f - fmaxf(hv, 0.0f));
+        const float scale = (1.0f - metal) * cos_theta / (prob_d * c_t);
+        wgt = f3((1.0f - fmaf(1.0f - f0.x, fr, f0.x)) * color.x * scale, (1.0f - fmaf(1.0f - f0.y, fr, f0.y)) * color.y * scale,
+                 (1.0f - fmaf(1.0f - f0.z, fr, f0.z)) * color.z * scale);
+    } else {
+        const float fr = pow5f(1.0f - hv);
+        const float a2 = rough * rough;
+        const float nh = dotf(normal, half);
+        float den = fmaf(nh * nh, a2 - 1.0f, 1.0f);
+        den = fmaxf(3.14159265358979323846f * den * den, 1e-7f);
+        const float D = a2 / den;
+        const float k = a2 * 0.125f;
+        const float nvs = dotf(normal, view);
+        const float nv = fmaxf(nvs, 0.0f), nl = fmaxf(ndl, 0.0f);
+        const float G = (nv / fmaf(nv, 1.0f - k, k)) * (nl / fmaf(nl, 1.0f - k, k));
+        const float denom = fmaf(4.0f * nvs, ndl, 0.001f);
+        const float pdf = fmaf(D * nh, 1.0f / (4.0f * hv), 0.0001f);
+        const float scale = (D * G) / denom * ndl / (1.0f - prob_d) / pdf;
+        wgt = f3(fmaf(1.0f - f0.x, fr, f0.x) * scale, fmaf(1.0f - f0.y, fr, f0.y) * scale, fmaf(1.0f - f0.z, fr, f0.z) * scale);
+    }
+    // |dir| = 1 to f32 accuracy; one Newton step of 1 / sqrt(|dir|^2) around 1 brings it to ~1e-14 without an f64 sqrt / division
+    const D3 dd = d3((double)dir.x, (double)dir.y, (double)dir.z);
+    dir_out = dd * (1.5 - 0.5 * dot(dd, dd));
+    wgt_out = d3((double)wgt.x, (double)wgt.y, (double)wgt.z);
+}
+
+// One bounce of `trace` (src/trace.rs:232-320) in throughput form: the recursion multiplies the
+// child radiance by a weight known before recursing, so a path's value is (prod of weights) (*)
+// emission.  Returns true when the path continues with (o, d, T) updated; otherwise `result` is
+// the radiance the path delivers.  PREC = rm_precision: the hit point, the surface normal and the next
+// origin are f64 in both modes; the lobe sampling and the BRDF weight follow PREC.
+template <int PREC>
+__device__ __forceinline__ bool shade(const DevScene& sc, const RenderParams& rp, double hit_t, int hit_obj, unsigned hit_sub, unsigned pixel,
+                                      unsigned sample, unsigned depth, D3& o, D3& d, D3& T, D3& result, unsigned& shaded_tri) {
+    result = d3(0.0, 0.0, 0.0);
+    if (hit_obj < 0) return false;                                          // :242
+    const DevObject& ob = sc.obj[hit_obj];
+    const D3 frag = o + d * hit_t;                                          // :246
+    if (ob.mat == RM_MATERIAL_EMISSION) { result = mul(T, ld3(ob.color)); return false; }   // :250
+    if (depth >= rp.bounce_limit) return false;                             // the child call returns 0 (:235-237)
+    D3 normal;                                                              // :244
+    if (ob.geom == GEOM_PLANE) normal = ld3(ob.g + 3);
+    else if (ob.geom == GEOM_SPHERE) normal = normalize(frag - ld3(ob.g));
+    else { normal = triangle_normal(sc.grid[ob.grid], hit_sub, frag); shaded_tri++; }
+    const D3 to_camera = ld3(rp.cam.pos) - frag;
+    const double metal = ob.mat == RM_MATERIAL_METAL ? 1.0 : 0.0;
+    D3 dir, wgt;
+    double eps;
+    if (PREC == RM_PRECISION_F32_SHADING) lobe_f32(rp, normal, to_camera, ld3(ob.color), ob.rough, metal, pixel, sample, depth, dir, wgt, eps);
+    else lobe_f64(rp, normal, to_camera, ld3(ob.color), ob.rough, metal, pixel, sample, depth, dir, wgt, eps);
     T = mul(T, wgt);
     if (T.x == 0.0 && T.y == 0.0 && T.z == 0.0) return false;   // nothing downstream can change a zero path value
     o = frag + normal * eps;
@@ -995,8 +1099,8 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
     }
 }
 
-// Stage part 3: shade, then deliver radiance or append the next ray (warp-aggregated compaction).
-template <bool FIRST>
+// Stage part 3: shade, then deliver radiance or append the next ray (warp-aggregated compaction) to the next depth's queue.
+template <bool FIRST, int PREC>
 __global__ void __launch_bounds__(kBlock, RM_SHADE_BLOCKS_PER_SM) k_shade(const __grid_constant__ DevScene sc, const __grid_constant__ RenderParams rp, const Queue qin,
                                                    const Queue qout, const HitArrays hit, const unsigned depth, const unsigned n_first) {
     const unsigned n = FIRST ? n_first : rp.cnt.rays[depth - 1];
@@ -1015,10 +1119,9 @@ __global__ void __launch_bounds__(kBlock, RM_SHADE_BLOCKS_PER_SM) k_shade(const 
             d = d3(qin.f[3][i], qin.f[4][i], qin.f[5][i]);
             T = FIRST ? d3(1.0, 1.0, 1.0) : d3(qin.f[6][i], qin.f[7][i], qin.f[8][i]);
             const unsigned q = slot % rp.n_pixels, s_local = slot / rp.n_pixels;
-            const unsigned pixel = rp.pixel_map[q];
-            const unsigned sample = rp.first_sample + s_local * rp.sample_stride;
             D3 result;
-            cont = shade(sc, rp, hit.t[i], hit.obj[i], hit.sub[i], pixel, sample, depth, o, d, T, result, shaded_tri);
+            cont = shade<PREC>(sc, rp, hit.t[i], hit.obj[i], hit.sub[i], rp.pixel_map[q], rp.first_sample + s_local * rp.sample_stride, depth, o, d, T, result,
+                               shaded_tri);
             if (!cont) {
                 rp.contrib[slot] = result.x;
                 rp.contrib[(size_t)rp.cap + slot] = result.y;

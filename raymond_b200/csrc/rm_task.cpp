@@ -118,6 +118,7 @@ void drive(rm_task* t) {
     const size_t total = split_samples ? (s.sample_count > first ? (s.sample_count - first + world - 1) / world : 0) : s.sample_count;
     const bool split_local = G > 1 && t->options.partition == RM_PARTITION_SAMPLES;
     int st = RM_OK;
+    Trace trace;
     // every checkpoint's frame of running sums lands in its own snapshot (a pinned block, cached across tasks: D2H at link
     // speed, and the messages slice their tiles straight out of it)
     try {
@@ -140,14 +141,17 @@ void drive(rm_task* t) {
             done += n;
             if (st == RM_OK && done < total) {
                 std::shared_ptr<FrameSnapshot> frame = new_snapshot(W, H);
-                st = reduce_accumulators_to_host(t->renderers.data(), (int)G, frame->sums);
+                st = reduce_accumulators_to_host(t->renderers.data(), (int)G, frame->sums, frame->pinned);
                 if (st == RM_OK) post_tiles(t, RM_TILE_PROGRESSED, done, frame);
             }
         }
+        trace.mark("driver: all launches enqueued");
         if (st == RM_OK) {
             std::shared_ptr<FrameSnapshot> frame = new_snapshot(W, H);
-            st = reduce_accumulators_to_host(t->renderers.data(), (int)G, frame->sums);
+            st = reduce_accumulators_to_host(t->renderers.data(), (int)G, frame->sums, frame->pinned);
+            trace.mark("driver: devices done, accumulators summed, frame on the host");
             if (st == RM_OK) post_tiles(t, RM_TILE_FINISHED, total, frame);      // src/trace.rs:211-212
+            trace.mark("driver: TileFinished messages posted");
         }
     } catch (const std::bad_alloc&) {
         st = fail(RM_ERR_OUT_OF_MEMORY, "out of host memory in the render driver");
@@ -161,6 +165,7 @@ void drive(rm_task* t) {
         stats.device_ms = std::max(stats.device_ms, one.device_ms);
         stats.upload_ms = std::max(stats.upload_ms, one.upload_ms);
     }
+    trace.mark("driver: statistics collected");
     std::lock_guard<std::mutex> lk(t->mu);
     t->stats = stats;
     t->status = st;
@@ -194,9 +199,11 @@ rm_task* rm_render_tiled(const rm_scene* scene, const rm_settings* settings, con
     for (size_t g = 0; g < G; g++) devices[g] = (t->options.device_list && t->options.device_count >= 1) ? t->options.device_list[g] : t->options.device + (int32_t)g;
     t->options.device_list = nullptr;
     t->options.device = devices[0];
-    // scene upload happens here, before the call returns, so a bad scene or a missing GPU is reported synchronously;
-    // the device copies are the snapshot (the caller may destroy `scene`).  The first GPU gets the scene from the host
-    // (flatten + one H2D copy); every other GPU gets a device-to-device copy of it, one host thread per GPU.
+    // Scene upload happens here, before the call returns, so a bad scene or a missing GPU is reported synchronously; the
+    // device copies are the snapshot (the caller may destroy `scene`).  One host thread per share: share 0 flattens the
+    // scene and uploads it (one H2D copy) while the other shares create their stream, pixel map, queues and accumulator;
+    // then every other share pulls the scene from the first device over NVLink (device-to-device, all at once).
+    Trace trace;
     t->renderers.assign(G, nullptr);
     std::vector<int> status(G, RM_OK);
     std::vector<std::string> errors(G);
@@ -207,27 +214,45 @@ rm_task* rm_render_tiled(const rm_scene* scene, const rm_settings* settings, con
         o.device_count = 0;
         return o;
     };
-    {
-        rm_gpu_options o = options_for(0);
-        t->renderers[0] = rm_renderer_create(scene, settings, &o);
-        if (!t->renderers[0]) { status[0] = rm_last_status(); errors[0] = rm_last_error(); }
-    }
-    if (t->renderers[0] && G > 1) {
-        rm_device_scene* first = rm_renderer_device_scene(t->renderers[0]);
-        auto create = [&](size_t g) {
-            rm_gpu_options o = options_for(g);
+    std::mutex first_mu;
+    std::condition_variable first_cv;
+    rm_device_scene* first = nullptr;
+    bool first_ready = false;
+    auto record = [&](size_t g) { status[g] = rm_last_status(); errors[g] = rm_last_error(); };
+    auto create = [&](size_t g) {
+        rm_gpu_options o = options_for(g);
+        if (g == 0) {
+            t->renderers[0] = rm_renderer_create(scene, settings, &o);
+            if (!t->renderers[0]) record(0);
+            std::lock_guard<std::mutex> lk(first_mu);
+            first = t->renderers[0] ? rm_renderer_device_scene(t->renderers[0]) : nullptr;
+            first_ready = true;
+            first_cv.notify_all();
+            return;
+        }
+        rm_renderer* r = rm_renderer_create_unbound(settings, &o);
+        if (!r) record(g);
+        {
+            std::unique_lock<std::mutex> lk(first_mu);
+            first_cv.wait(lk, [&] { return first_ready; });
+        }
+        if (r && first) {
             rm_device_scene* ds = rm_device_scene_clone_to(first, o.device);
-            if (ds) {
-                t->renderers[g] = rm_renderer_create_owning(ds, settings, &o);
-                if (!t->renderers[g]) rm_device_scene_destroy(ds);
-            }
-            if (!t->renderers[g]) { status[g] = rm_last_status(); errors[g] = rm_last_error(); }
-        };
+            if (ds) rm_renderer_bind_scene(r, ds, 1);
+            else { record(g); rm_renderer_destroy(r); r = nullptr; }
+        } else if (r) {
+            rm_renderer_destroy(r);
+            r = nullptr;
+        }
+        t->renderers[g] = r;
+    };
+    {
         std::vector<std::thread> pool;
-        for (size_t g = 2; g < G; g++) pool.emplace_back(create, g);
-        create(1);
+        for (size_t g = 1; g < G; g++) pool.emplace_back(create, g);
+        create(0);
         for (std::thread& th : pool) th.join();
     }
+    trace.mark("rm_render_tiled: scene resident and renderers ready on every device");
     for (size_t g = 0; g < G; g++)
         if (!t->renderers[g] && (g == 0 || t->renderers[0])) {
             for (rm_renderer* r : t->renderers) rm_renderer_destroy(r);
@@ -256,8 +281,10 @@ int rm_task_poll(rm_task* t, rm_message* out) {
 
 int rm_task_await(rm_task* t, rm_vec3* out) {
     if (!t || !out) return fail(RM_ERR_INVALID_ARGUMENT, "rm_task_await: null argument");
+    Trace trace;
     std::unique_lock<std::mutex> lk(t->mu);
     t->cv.wait(lk, [&] { return t->finished; });
+    trace.mark("await: render finished");
     if (t->status != RM_OK) return fail(t->status, t->error);
     const size_t W = t->settings.camera_settings.backbuffer_width, H = t->settings.camera_settings.backbuffer_height;
     // drain: TileProgressed messages are skipped, not a stop (the reference breaks at the first one, src/trace.rs:101-103)
@@ -287,6 +314,7 @@ int rm_task_await(rm_task* t, rm_vec3* out) {
     for (size_t w = 1; w < workers; w++) pool.emplace_back(rows, H * w / workers, H * (w + 1) / workers);
     rows(0, H / workers);
     for (std::thread& th : pool) th.join();
+    trace.mark("await: averaged frame written");
     return RM_OK;
 }
 

@@ -5,6 +5,8 @@ import numpy as np
 from raymond_b200 import api as A, fixtures as F
 
 spp = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+# argv[2]: device list of the render_tiled leg, e.g. "0,0,0,0" (four shares on GPU 0) or "0,1,2,3,4,5,6,7"
+devices = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else None
 objs = F.gold_dragon(F.dragon_standin())
 cam = F.camera(1920, 1080)
 t = time.perf_counter(); scene = A.Scene.from_fixture(objs); print(f"host scene build {time.perf_counter()-t:.3f}s")
@@ -18,7 +20,7 @@ for rep in range(3):
     del ds; t6 = time.perf_counter()
     print(f"rep {rep}: device scene {t1-t0:.3f}  renderer create {t2-t1:.3f}  render {t3-t2:.3f}  read_frame {t4-t3:.3f}  renderer close {t5-t4:.3f}  scene destroy {t6-t5:.3f}")
 for rep in range(3):
-    t0 = time.perf_counter(); task = A.render_tiled(scene, st, A.GpuOptions(seed=rep)); t1 = time.perf_counter()
+    t0 = time.perf_counter(); task = A.render_tiled(scene, st, A.GpuOptions(seed=rep, device_list=devices)); t1 = time.perf_counter()
     s = task.stats(); t2 = time.perf_counter()
     out = task.await_(); t3 = time.perf_counter()
     del task; t4 = time.perf_counter()

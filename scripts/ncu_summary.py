@@ -35,6 +35,9 @@ def raw(rep):
 def source(rep, launch, top):
     out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--kernel-id', f':::{launch}'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
+    if len(rows) < 3:          # a report with a single launch
+        out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(out)))
     hdr = rows[1]
     data = [r for r in rows[2:] if len(r) == len(hdr) and r[0].startswith('0x')]
     data = data[:len(data) // 2] if len(data) > 1 and data[0][0] == data[len(data) // 2][0] else data

@@ -1,4 +1,6 @@
-# run scripts/stage_times.py for the main library and every build_variants/*.so
+# time the build variants under build_variants/*.so (made here with raymond_b200.build.build(defines=..., out=...)) on the GPU box
 for lib in raymond_b200/libraymond_cuda.so build_variants/*.so; do
-  printf "%-36s " $(basename $lib); RAYMOND_CUDA_LIB=$PWD/$lib timeout 120 python scripts/stage_times.py ${1:-16} 2>&1 | tail -1
+  for p in f64 f32shade; do
+    RAYMOND_CUDA_LIB=$PWD/$lib python scripts/stage_times.py 32 $p dragon 2>&1 | tail -1
+  done
 done
