@@ -434,6 +434,28 @@ def bench_ours(args):
     dr.close()
     del dr
 
+    # ---- the same frame with the statistical scope (BRDF sampling / weights) in f32 (rm_precision 1), reported beside the headline
+    f32_mode = None
+    if not args.no_extras and precision == 0:
+        d32 = D.DistributedRenderer(scene, settings, device=local, seed=args.seed, precision=A.PRECISION_F32_SHADING)
+        d32.render(spp); d32.checkpoint(); d32.synchronize()
+        n32 = max(1, min(args.steps, 3))
+        barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(d32.stream)
+        for _ in range(n32):
+            d32.clear(); d32.render(spp); d32.checkpoint()
+        e1.record(d32.stream)
+        torch.cuda.synchronize(); barrier()
+        ms32 = max_over_ranks(e0.elapsed_time(e1))
+        f32frame = d32.frame(spp)
+        f32_mode = {"value": W * H * spp * n32 / ms32 / 1e3, "unit": UNIT, "ms_per_step": ms32 / n32, "steps": n32,
+                    "mean_radiance": None if f32frame is None else [float(x) for x in f32frame.mean(axis=(0, 1))],
+                    "what": "rm_gpu_options.precision = RM_PRECISION_F32_SHADING: lobe sampling, Fresnel, GGX and Smith terms in f32 with FMA; camera rays, "
+                            "Scene::intersect, hit points, normals and ray origins stay the reference's f64 sequence (tests: noise floor of SURVEY 8d)"}
+        d32.close()
+        del d32
+
     # ---- BASELINE configs[2] and configs[4] at this N (scene resident, exchange inside, wall clock around barriers, max over ranks)
     other = None
     if not args.no_extras:
@@ -535,7 +557,7 @@ def bench_ours(args):
             "dtype": "f64" if args.precision == "f64" else "f64 intersection + f32 shading", "data": "synthetic",
             "config": config_of(args, label),
             "e2e": e2e, "e2e_torchrun": e2e_torchrun, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "other_configs": other,
+            "other_configs": other, "f32_shading": f32_mode,
             "mrays_per_s": rays / ms_total / 1e3, "rays_per_path": rays / max(samples_total, 1),
             "stages": stages, "host_grid_build_s": host_build_s, "mean_radiance": mean_radiance,
             "nonfinite_samples": int(s1["nonfinite_samples"]),

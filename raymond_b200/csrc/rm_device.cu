@@ -535,7 +535,10 @@ static int renderer_init(rm_renderer* r) {
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) target = std::min(target, std::max<size_t>(free_b / 4 / 328, (size_t)1 << 20));
         spp = npix ? std::max<size_t>(1, target / npix) : 1;
         spp = std::min<size_t>(spp, 64);
-        spp = std::min<size_t>(spp, std::max<size_t>(s.sample_count, 1));
+        // ... and never more than this share of the job renders (a rank / device of a sample-split job gets 1 / world_size of them)
+        size_t own = std::max<size_t>(s.sample_count, 1);
+        if (r->opt.world_size > 1 && r->opt.partition == RM_PARTITION_SAMPLES) own = (own + (size_t)r->opt.world_size - 1) / (size_t)r->opt.world_size;
+        spp = std::min<size_t>(spp, own);
     }
     while (spp > 1 && spp * npix >= 0xffffffffull) spp--;
     r->batch_spp = spp;

@@ -20,7 +20,7 @@ LUMA = np.array([0.2126, 0.7152, 0.0722])
 
 
 def gpu_render(objs, cam, spp, seed=0, **kw):
-    opts = A.GpuOptions(seed=seed, **{k: v for k, v in kw.items() if k in ("rank", "world_size", "partition", "batch_spp", "flags")})
+    opts = A.GpuOptions(seed=seed, **{k: v for k, v in kw.items() if k in ("rank", "world_size", "partition", "batch_spp", "flags", "precision")})
     st = settings(cam, spp, bounce_limit=kw.get("bounce_limit", 5))
     r = A.Renderer(product_scene(objs), st, opts)
     r.render(kw.get("first", 0), kw.get("count", spp), kw.get("stride", 1))
@@ -68,13 +68,15 @@ def test_baseline_config_c1_same_stream():
     assert gs["samples"] == oc["samples"] == 320 * 240 * 16
 
 
-def test_reflective_spheres_noise_floor():
-    """RMSE(GPU, oracle seed A) <= 1.15 RMSE(oracle seed B, oracle seed A) per channel, different streams."""
+@pytest.mark.parametrize("precision", [A.PRECISION_F64, A.PRECISION_F32_SHADING], ids=["f64", "f32shade"])
+def test_reflective_spheres_noise_floor(precision):
+    """RMSE(GPU, oracle seed A) <= 1.15 RMSE(oracle seed B, oracle seed A) per channel, different streams.
+    Both arithmetic modes of the statistical scope (rm_precision) are held to it."""
     objs, cam, spp = F.reflective_spheres(), F.camera(128, 96), 32
     sc = oracle_scene(objs)
     a, _ = O.render(sc, cam, spp, seed=11)
     b, _ = O.render(sc, cam, spp, seed=12)
-    g, _ = gpu_render(objs, cam, spp, seed=13)
+    g, _ = gpu_render(objs, cam, spp, seed=13, precision=precision)
     clip = lambda x: np.clip(x / spp, 0, 10)
     rmse0 = np.sqrt(((clip(a) - clip(b)) ** 2).mean(axis=(0, 1)))
     rmse = np.sqrt(((clip(g) - clip(a)) ** 2).mean(axis=(0, 1)))
