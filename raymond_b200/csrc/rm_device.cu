@@ -690,17 +690,21 @@ struct SharePointers {
     const double* acc[kMaxShares];
     int count;
 };
-__global__ void __launch_bounds__(256) k_reduce_slice(const __grid_constant__ SharePointers p, double* __restrict__ out, size_t begin, size_t end) {
+// `mean` (optional): the finalize fused in — tile.data[..] / tile.sample_count as f64 (src/trace.rs:95), so that await() only copies.
+__global__ void __launch_bounds__(256) k_reduce_slice(const __grid_constant__ SharePointers p, double* __restrict__ out, double* __restrict__ mean,
+                                                        double divisor, size_t begin, size_t end) {
     for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (size_t)gridDim.x * blockDim.x) {
         double s = p.acc[0][i];
         for (int j = 1; j < p.count; j++) s += p.acc[j][i];
         out[i] = s;
+        if (mean) mean[i] = s / divisor;
     }
 }
 
 static int reduce_gather_to_host(rm_renderer* const* rs, int count, rm_vec3* out);
 
-int reduce_accumulators_to_host(rm_renderer* const* rs, int count, rm_vec3* out, bool out_is_pinned) {
+int reduce_accumulators_to_host(rm_renderer* const* rs, int count, rm_vec3* out, bool out_is_pinned, rm_vec3* mean_pinned, double divisor, bool* mean_written) {
+    if (mean_written) *mean_written = false;
     if (count <= 0 || !rs || !out) return fail(RM_ERR_INVALID_ARGUMENT, "reduce_accumulators_to_host: bad argument");
     rm_renderer* r0 = rs[0];
     const size_t n = r0->settings.camera_settings.backbuffer_width * r0->settings.camera_settings.backbuffer_height * 3;
@@ -720,9 +724,10 @@ int reduce_accumulators_to_host(rm_renderer* const* rs, int count, rm_vec3* out,
             }
         }
     // the frame as the devices see it (the same address under unified addressing)
-    double* out_dev = nullptr;
+    double *out_dev = nullptr, *mean_dev = nullptr;
     RM_CUDA(cudaSetDevice(r0->device));
     if (cudaHostGetDevicePointer((void**)&out_dev, (void*)out, 0) != cudaSuccess) { cudaGetLastError(); return reduce_gather_to_host(rs, count, out); }
+    if (mean_pinned && cudaHostGetDevicePointer((void**)&mean_dev, (void*)mean_pinned, 0) != cudaSuccess) { cudaGetLastError(); mean_dev = nullptr; }
     SharePointers p{};
     p.count = count;
     for (int g = 0; g < count; g++) p.acc[g] = rs[g]->accum;
@@ -740,7 +745,7 @@ int reduce_accumulators_to_host(rm_renderer* const* rs, int count, rm_vec3* out,
         const size_t begin = (n * (size_t)g / (size_t)count) & ~(size_t)31, end = g + 1 == count ? n : (n * (size_t)(g + 1) / (size_t)count) & ~(size_t)31;
         if (end > begin) {
             const unsigned blocks = (unsigned)std::min<size_t>((end - begin + 255) / 256, (size_t)r->sms * 8);
-            k_reduce_slice<<<blocks, 256, 0, r->stream>>>(p, out_dev, begin, end);
+            k_reduce_slice<<<blocks, 256, 0, r->stream>>>(p, out_dev, mean_dev, divisor, begin, end);
             r->launches++;
         }
         RM_CUDA(cudaGetLastError());
@@ -756,6 +761,7 @@ int reduce_accumulators_to_host(rm_renderer* const* rs, int count, rm_vec3* out,
         cudaError_t e = cudaEventSynchronize(rs[g]->ev_reduced);
         if (e != cudaSuccess) return fail(RM_ERR_CUDA, std::string("accumulator exchange: ") + cudaGetErrorString(e));
     }
+    if (mean_written) *mean_written = mean_dev != nullptr;
     return RM_OK;
 }
 

@@ -86,7 +86,10 @@ std::vector<TileRect> tile_layout(size_t W, size_t H, size_t tw, size_t th);
 // destination every device sums its slice of the frame from all peers' accumulators in place (peer reads over NVLink) and
 // writes it straight to the host; otherwise the sums are gathered onto the first device and copied.  Either way the sum
 // is taken in renderer order, the renderers' accumulators are left as they are, and on return the frame is complete.
-int reduce_accumulators_to_host(rm_renderer* const* renderers, int count, rm_vec3* out, bool out_is_pinned);
+// `mean_pinned` (optional, pinned): the peer-memory path also writes sum / divisor there (the finalize of await(), fused into
+// the exchange) and sets *mean_written; the other paths leave it alone.
+int reduce_accumulators_to_host(rm_renderer* const* renderers, int count, rm_vec3* out, bool out_is_pinned, rm_vec3* mean_pinned = nullptr,
+                                double divisor = 1.0, bool* mean_written = nullptr);
 // display transform kernel (rm_display.cu): sums / divisor -> tonemap -> 8-bit RGB, device pointers
 int tonemap_device(const double* sums_device, size_t n_pixels, double divisor, double exposure, double gamma, unsigned char* out_device, void* stream);
 int dev_alloc(void** p, size_t bytes);

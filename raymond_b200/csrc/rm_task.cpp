@@ -16,6 +16,8 @@ using namespace rm;
 struct FrameSnapshot {
     rm_vec3* sums = nullptr;        // W * H, row-major: the pinned block the D2H copy landed in (pageable when pinning fails
     bool pinned = false;            // or too much is already held by undelivered checkpoints)
+    rm_vec3* mean = nullptr;        // final frame of a multi-device task: sums / sample_count, written by the exchange kernel (pinned)
+    bool has_mean = false;
     size_t bytes = 0;
     size_t W = 0;
     FrameSnapshot() = default;
@@ -69,6 +71,7 @@ std::shared_ptr<FrameSnapshot> new_snapshot(size_t W, size_t H) {
 FrameSnapshot::~FrameSnapshot() {
     if (pinned) { pinned_release(sums); g_snapshot_pinned_bytes -= bytes; }
     else free(sums);
+    if (mean) { pinned_release(mean); g_snapshot_pinned_bytes -= bytes; }
 }
 
 namespace {
@@ -148,7 +151,12 @@ void drive(rm_task* t) {
         trace.mark("driver: all launches enqueued");
         if (st == RM_OK) {
             std::shared_ptr<FrameSnapshot> frame = new_snapshot(W, H);
-            st = reduce_accumulators_to_host(t->renderers.data(), (int)G, frame->sums, frame->pinned);
+            // several devices: the exchange kernel also writes the averaged frame await() hands out (the finalize, fused in)
+            if (G > 1 && frame->pinned && t->options.partition == RM_PARTITION_SAMPLES && g_snapshot_pinned_bytes.load() + frame->bytes <= kSnapshotPinnedLimit) {
+                frame->mean = (rm_vec3*)pinned_acquire(frame->bytes);
+                if (frame->mean) g_snapshot_pinned_bytes += frame->bytes;
+            }
+            st = reduce_accumulators_to_host(t->renderers.data(), (int)G, frame->sums, frame->pinned, frame->mean, (double)total, &frame->has_mean);
             trace.mark("driver: devices done, accumulators summed, frame on the host");
             if (st == RM_OK) post_tiles(t, RM_TILE_FINISHED, total, frame);      // src/trace.rs:211-212
             trace.mark("driver: TileFinished messages posted");
@@ -296,7 +304,19 @@ int rm_task_await(rm_task* t, rm_vec3* out) {
     lk.unlock();
     // out[x + left + (y + top) * W] = tile.data[..] / tile.sample_count as f64      src/trace.rs:95-97 — pixels no finished tile
     // covers (another rank's tiles) stay zero; rows are divided by a few host threads
+    // every finished tile comes from one snapshot that already holds the averaged frame (multi-device exchange): copy rows
+    const FrameSnapshot* whole = nullptr;
+    if (!finished.empty() && finished[0].frame->has_mean) {
+        size_t covered = 0;
+        whole = finished[0].frame.get();
+        for (const PendingMessage& m : finished) {
+            if (m.frame.get() != whole) { whole = nullptr; break; }
+            covered += m.rect.width * m.rect.height;
+        }
+        if (covered != W * H) whole = nullptr;
+    }
     auto rows = [&](size_t y0, size_t y1) {
+        if (whole) { memcpy((void*)(out + y0 * W), (const void*)(whole->mean + y0 * W), (y1 - y0) * W * sizeof(rm_vec3)); return; }
         for (size_t y = y0; y < y1; y++) memset((void*)(out + y * W), 0, W * sizeof(rm_vec3));
         for (const PendingMessage& m : finished) {
             const double c = (double)m.sample_count;

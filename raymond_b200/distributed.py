@@ -64,6 +64,19 @@ def reduce_sums(accum, dst: int = 0):
     return accum
 
 
+_pinned_frames = {}
+
+
+def pinned_frame(shape):
+    """A page-locked (H, W, 3) f64 host buffer, one per shape and process, kept for the life of the process: pinning 50 MB
+    costs ~10 ms, more than the copy it serves."""
+    import torch
+    key = tuple(shape)
+    if key not in _pinned_frames:
+        _pinned_frames[key] = torch.empty(key, dtype=torch.float64, pin_memory=True)
+    return _pinned_frames[key]
+
+
 class AccumulatorExchange:
     """The non-destructive accumulator exchange: `checkpoint(accum)` sums a scratch copy of every rank's running sums
     onto rank 0 and leaves `accum` alone, so it can be called any number of times during a render."""
@@ -111,7 +124,7 @@ class DistributedRenderer:
             self.stream = torch.cuda.Stream(device=device)
             self.accum = torch.zeros((cs.backbuffer_height, cs.backbuffer_width, 3), dtype=torch.float64, device=f"cuda:{device}")
             self.exchange = AccumulatorExchange(self.accum)
-            self._host = torch.empty(self.accum.shape, dtype=torch.float64, pin_memory=True) if self.rank == 0 else None
+            self._host = pinned_frame(self.accum.shape) if self.rank == 0 else None
         opts = A.GpuOptions(device=device, rank=self.rank, world_size=self.world_size, partition=partition, seed=seed,
                             stream=self.stream.cuda_stream, accum_device=self.accum.data_ptr(), batch_spp=batch_spp, flags=flags,
                             precision=precision)
@@ -144,7 +157,8 @@ class DistributedRenderer:
         self.stream.synchronize()
 
     def sums(self) -> Optional[np.ndarray]:
-        """checkpoint() brought to rank 0's host: the (H, W, 3) running sums of the whole job (None on the other ranks)."""
+        """checkpoint() brought to rank 0's host: the (H, W, 3) running sums of the whole job (None on the other ranks).
+        The array is a view of a pinned buffer shared by the renderers of this process: copy it to keep it past the next call."""
         total = self.checkpoint()
         if total is None:
             self.stream.synchronize()
