@@ -5,7 +5,7 @@ TAG=${1:-r1}
 KREGEX=${2:-k_traverse}
 SKIP=${3:-5}
 COUNT=${4:-3}
-CMD="python bench.py --spp 16 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"
+CMD="python bench.py --spp 16 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-extras"
 timeout 900 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err; echo "ref rc=$?"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu1_$TAG.log 2>&1

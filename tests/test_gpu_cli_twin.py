@@ -40,3 +40,54 @@ def test_cli_old_twin(tmp_path):
     frame = A.render_tiled(scene, settings(F.camera(160, 90), 6), A.GpuOptions(seed=11)).await_()
     assert np.array_equal(got, A.tonemap(frame))
     assert (got.reshape(-1, 3).max(axis=0) > 200).all() and got.shape == (90, 160, 3)
+
+
+def test_cli_old_twin_streams_tile_messages(tmp_path):
+    """--serve: the reference's intended server role (server/src/main.rs:174-192, protocol.rs:9-14) — every Message of a
+    progressive render on a TCP socket, one JSON text per "\\r\\n"-terminated line, in the order TaskHandle::poll delivers them."""
+    import json
+    import socket
+    import time
+    exe = str(tmp_path / "cli_old")
+    lib_dir = os.path.join(ROOT, "raymond_b200")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "cli_old.cpp"),
+                    "-L", lib_dir, "-lraymond_cuda", f"-Wl,-rpath,{lib_dir}", "-o", exe], check=True)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    W, H, spp, spi, seed = 96, 64, 6, 2, 4
+    out = str(tmp_path / "served.png")
+    proc = subprocess.Popen([exe, "--out", out, "--width", str(W), "--height", str(H), "--spp", str(spp), "--spi", str(spi), "--seed", str(seed),
+                             "--serve", str(port)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    conn = None
+    for _ in range(200):
+        try:
+            conn = socket.create_connection(("127.0.0.1", port), timeout=60)
+            break
+        except OSError:
+            time.sleep(0.05)
+    assert conn is not None, "the twin never listened"
+    data = b""
+    while chunk := conn.recv(1 << 20):
+        data += chunk
+    conn.close()
+    assert proc.wait(timeout=120) == 0, proc.stderr.read()
+    lines = data.split(b"\r\n")
+    assert lines[-1] == b""
+    msgs = [json.loads(l) for l in lines[:-1]]
+    st = settings(F.camera(W, H), spp, spi=spi)
+    layout = [tuple(r) for r in A.tile_layout(st)]
+    assert [m["type"] for m in msgs] == ["TileProgressed"] * (2 * len(layout)) + ["TileFinished"] * len(layout)
+    assert [m["data"]["sample_count"] for m in msgs] == [2] * len(layout) + [4] * len(layout) + [6] * len(layout)
+    assert [(m["data"]["left"], m["data"]["top"], m["data"]["width"], m["data"]["height"]) for m in msgs[-len(layout):]] == layout
+    assert list(msgs[0]["data"].keys()) == ["sample_count", "width", "height", "left", "top", "data"]       # core/src/tile.rs:6-14 field order
+    # the tiles on the wire are the running sums of the same render through the Python mirror (exact f64 round trip)
+    r = A.Renderer(A.Scene.from_fixture(F.reflective_spheres()), st, A.GpuOptions(seed=seed))
+    r.render(0, spp)
+    want = r.read_sums()
+    r.close()
+    for m in msgs[-len(layout):]:
+        t = m["data"]
+        got = np.array([[p["x"], p["y"], p["z"]] for p in t["data"]]).reshape(t["height"], t["width"], 3)
+        assert np.array_equal(got, want[t["top"]:t["top"] + t["height"], t["left"]:t["left"] + t["width"]])
+    assert os.path.exists(out)
