@@ -9,6 +9,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <type_traits>
 #include <vector>
 
@@ -33,9 +34,10 @@ static int sm_count(int device) {
 // other libraries in the process may use, is left alone).  The pool keeps up to kPoolKeepBytes of freed memory mapped, so the
 // multi-GB wavefront queues of one render are handed to the next one instead of being unmapped and re-mapped (cudaFree /
 // cudaMalloc of 10 GB cost 0.1-0.5 s each); anything beyond that goes back to the driver at the next synchronisation, and
-// rm_release_cached_memory() returns all of it.  Peers that can reach the device get read/write access to the pool: the
-// accumulator exchange of a multi-GPU task reads peer accumulators directly over NVLink.  All pool traffic is ordered on
-// the legacy default stream; users synchronise their own stream before dev_free().
+// rm_release_cached_memory() returns all of it.  The pool is private to its device (granting peers access to a whole pool made
+// growing it fail on multi-GPU boxes); the one buffer peers read directly — the accumulator — is a plain cudaMalloc
+// allocation, reachable through cudaDeviceEnablePeerAccess.  All pool traffic is ordered on the legacy default stream; users
+// synchronise their own stream before dev_free().
 namespace {
 constexpr unsigned long long kPoolKeepBytes = 48ull << 30;
 std::mutex g_pool_mu;
@@ -56,17 +58,6 @@ static cudaError_t device_pool(int dev, cudaMemPool_t* out) {
     if (e != cudaSuccess) return e;
     unsigned long long keep = kPoolKeepBytes;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    int count = 0;
-    cudaGetDeviceCount(&count);
-    for (int peer = 0; peer < count; peer++) {
-        int can = 0;
-        if (peer == dev || cudaDeviceCanAccessPeer(&can, peer, dev) != cudaSuccess || !can) continue;
-        cudaMemAccessDesc desc{};
-        desc.location.type = cudaMemLocationTypeDevice;
-        desc.location.id = peer;
-        desc.flags = cudaMemAccessFlagsProtReadWrite;
-        cudaMemPoolSetAccess(pool, &desc, 1);
-    }
     cudaGetLastError();
     g_pools[dev] = pool;
     *out = pool;
@@ -80,6 +71,18 @@ static cudaError_t dev_malloc_raw(void** p, size_t bytes) {
     if (e == cudaSuccess) e = device_pool(dev, &pool);
     if (e == cudaSuccess) e = cudaMallocFromPoolAsync(p, std::max<size_t>(bytes, 32), pool, 0);
     if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    if (e == cudaErrorMemoryAllocation && pool) {
+        // say what the device and the pool hold: an out-of-memory here is usually memory cached or in use elsewhere in the process
+        size_t free_b = 0, total_b = 0;
+        unsigned long long reserved = 0, used = 0;
+        cudaGetLastError();
+        cudaMemGetInfo(&free_b, &total_b);
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+        fprintf(stderr, "[raymond] device %d: allocation of %zu bytes failed; device free %zu of %zu, pool reserved %llu, pool in use %llu\n", dev, bytes, free_b,
+                total_b, reserved, used);
+        cudaGetLastError();
+    }
     return e;
 }
 template <typename T>
@@ -88,6 +91,45 @@ static void dev_free(void* p) { if (p) cudaFreeAsync(p, 0); }
 
 int dev_alloc(void** p, size_t bytes) { return (int)dev_malloc_raw(p, bytes); }
 void dev_release(void* p) { dev_free(p); }
+
+// ---- accumulators: plain cudaMalloc blocks (peers read them in place through cudaDeviceEnablePeerAccess), kept per device for the
+// next renderer — with peer access on, cudaMalloc / cudaFree of 50 MB map and unmap on every peer and cost milliseconds
+namespace {
+struct AccumBlock { int device; size_t bytes; void* p; };
+std::mutex g_accum_mu;
+std::vector<AccumBlock>& g_accum_free = *new std::vector<AccumBlock>();      // never destroyed (frees device memory)
+constexpr size_t kAccumCacheBytes = (size_t)2 << 30;
+}  // namespace
+
+static cudaError_t accum_acquire(int device, size_t bytes, double** out) {
+    {
+        std::lock_guard<std::mutex> lk(g_accum_mu);
+        for (size_t i = 0; i < g_accum_free.size(); i++)
+            if (g_accum_free[i].device == device && g_accum_free[i].bytes == bytes) {
+                *out = (double*)g_accum_free[i].p;
+                g_accum_free.erase(g_accum_free.begin() + (long)i);
+                return cudaSuccess;
+            }
+    }
+    return cudaMalloc(out, bytes);
+}
+
+static void accum_release(int device, size_t bytes, void* p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_accum_mu);
+        size_t cached = 0;
+        for (const AccumBlock& b : g_accum_free) cached += b.bytes;
+        if (cached + bytes <= kAccumCacheBytes) { g_accum_free.push_back({device, bytes, p}); return; }
+    }
+    cudaFree(p);
+}
+
+static void accum_cache_clear() {
+    std::lock_guard<std::mutex> lk(g_accum_mu);
+    for (const AccumBlock& b : g_accum_free) { cudaSetDevice(b.device); cudaFree(b.p); }
+    g_accum_free.clear();
+}
 
 // ---- pinned staging pool
 namespace {
@@ -151,6 +193,14 @@ static DevCamera make_camera(const rm_camera_settings& c) {
     return d;
 }
 
+// Owned pixels of a share in launch order, resident on one device (see pixel_map_for).
+struct PixelMap {
+    unsigned* dev = nullptr;
+    size_t n = 0;
+    int device = 0;
+    ~PixelMap();
+};
+
 // Device buffers one batch of rays needs for Scene::intersect: hit records and the traversal queue.
 struct IntersectBuffers {
     HitArrays hit{};
@@ -210,10 +260,20 @@ __global__ void __launch_bounds__(256) k_spread_spheres(const float4* __restrict
         per_reference[p] = __ldg(&per_triangle[__ldg(&refs[p])]);
 }
 
-// One device allocation + one H2D copy per grid: the flattened arrays are written straight into ONE pinned
-// staging block (cached across calls) laid out like the device block, by a few host threads.
-static int upload_grid(rm_device_scene* ds, const Grid& g, DevGrid* out) {
-    DevGrid d{};
+// The flattened image of one grid: the arrays of DevGrid laid out in ONE block — [tri][shd][cells][occ][refs][one sphere per
+// triangle] come from the host, [one sphere per reference] behind them is spread on the device (k_spread_spheres), so it never
+// crosses the bus.  The host image of an immutable grid is built once by a few host threads and kept (pinned) with the grid;
+// images above kImageCacheLimit are staged through a pooled pinned block per upload.
+struct GridImage {
+    DevGrid header{};          // geometry of the grid; the array pointers are set by point_grid()
+    size_t off_tri = 0, off_shd = 0, off_cells = 0, off_occ = 0, off_refs = 0, off_spht = 0, host_total = 0, off_sph = 0, total = 0, nr = 0;
+    char* host = nullptr;
+    bool cached = false;       // the host image belongs to the grid (not released after the upload)
+};
+
+static int prepare_grid_image(const Grid& g, GridImage* out) {
+    GridImage& im = *out;
+    DevGrid& d = im.header;
     d.bmin[0] = g.bounds.min.x; d.bmin[1] = g.bounds.min.y; d.bmin[2] = g.bounds.min.z;
     d.bmax[0] = g.bounds.max.x; d.bmax[1] = g.bounds.max.y; d.bmax[2] = g.bounds.max.z;
     d.cell[0] = g.cell_size.x; d.cell[1] = g.cell_size.y; d.cell[2] = g.cell_size.z;
@@ -225,25 +285,32 @@ static int upload_grid(rm_device_scene* ds, const Grid& g, DevGrid* out) {
     const size_t nc = (size_t)d.n_cells, nt = g.triangles.size(), nr = g.references.size();
     const size_t n_occ = (nc + 31) / 32;
     auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    // device block: [tri][shd][cells][occ][refs][one sphere per triangle] come from the host in one copy; [one sphere per
-    // reference] behind them is spread on the device (k_spread_spheres), so it never crosses the bus
-    const size_t off_tri = 0, off_shd = off_tri + pad(nt * 12 * sizeof(double)), off_cells = off_shd + pad(nt * 18 * sizeof(double)),
-                 off_occ = off_cells + pad(nc * sizeof(uint2)), off_refs = off_occ + pad(n_occ * sizeof(unsigned)),
-                 off_spht = off_refs + pad(nr * sizeof(unsigned)), host_total = off_spht + pad(nt * sizeof(float4)) + 256,
-                 off_sph = host_total, total = off_sph + pad(nr * sizeof(float4)) + 256;
-    // the flattened image of an immutable grid is built once and kept (pinned) with the grid; bigger ones are staged per upload
+    im.nr = nr;
+    im.off_tri = 0;
+    im.off_shd = im.off_tri + pad(nt * 12 * sizeof(double));
+    im.off_cells = im.off_shd + pad(nt * 18 * sizeof(double));
+    im.off_occ = im.off_cells + pad(nc * sizeof(uint2));
+    im.off_refs = im.off_occ + pad(n_occ * sizeof(unsigned));
+    im.off_spht = im.off_refs + pad(nr * sizeof(unsigned));
+    im.host_total = im.off_spht + pad(nt * sizeof(float4)) + 256;
+    im.off_sph = im.host_total;
+    im.total = im.off_sph + pad(nr * sizeof(float4)) + 256;
+    const size_t host_total = im.host_total;
     std::unique_lock<std::mutex> image_lock(g.image_mu);
     const bool have_image = g.image && g.image_bytes == host_total;
     const bool keep_image = have_image || (host_total <= kImageCacheLimit && Grid::g_grid_image_bytes.load() + host_total <= kImageCacheTotalLimit);
     if (!keep_image) image_lock.unlock();
     char* host = have_image ? (char*)g.image : (char*)pinned_acquire(host_total);
     if (!host) return fail(RM_ERR_OUT_OF_MEMORY, "cannot pin " + std::to_string(host_total) + " bytes of host staging memory");
-    double* tri = (double*)(host + off_tri);
-    double* shd = (double*)(host + off_shd);
-    float4* sph_tri = (float4*)(host + off_spht);      // one bounding sphere per triangle
-    uint2* cells = (uint2*)(host + off_cells);
-    unsigned* occ = (unsigned*)(host + off_occ);
-    unsigned* refs = (unsigned*)(host + off_refs);
+    im.host = host;
+    im.cached = keep_image;
+    if (have_image) return RM_OK;
+    double* tri = (double*)(host + im.off_tri);
+    double* shd = (double*)(host + im.off_shd);
+    float4* sph_tri = (float4*)(host + im.off_spht);      // one bounding sphere per triangle
+    uint2* cells = (uint2*)(host + im.off_cells);
+    unsigned* occ = (unsigned*)(host + im.off_occ);
+    unsigned* refs = (unsigned*)(host + im.off_refs);
 
     auto fill_triangles = [&](size_t lo, size_t hi) {
         for (size_t i = lo; i < hi; i++) {
@@ -289,60 +356,71 @@ static int upload_grid(rm_device_scene* ds, const Grid& g, DevGrid* out) {
             occ[w] = bits;
         }
     };
-    if (!have_image) {
-        const unsigned hw = std::thread::hardware_concurrency();
-        const size_t workers = (nt + nc + nr < ((size_t)1 << 18)) ? 1 : std::min<size_t>(hw ? hw : 4, 8);
-        std::vector<std::thread> pool;
-        for (size_t w = 1; w < workers; w++)
-            pool.emplace_back([&, w] {
-                fill_triangles(nt * w / workers, nt * (w + 1) / workers);
-                fill_cells((nc * w / workers) & ~(size_t)31, w + 1 == workers ? nc : (nc * (w + 1) / workers) & ~(size_t)31);
-            });
-        fill_triangles(0, nt / workers);
-        fill_cells(0, workers == 1 ? nc : (nc / workers) & ~(size_t)31);
-        if (nr) memcpy(refs, g.references.data(), nr * sizeof(unsigned));
-        for (std::thread& t : pool) t.join();
-        if (keep_image) { g.image = host; g.image_bytes = host_total; Grid::g_grid_image_bytes += host_total; }
-    }
-    if (keep_image) image_lock.unlock();       // the image is read-only from here on
-    void* dev = nullptr;
-    cudaError_t e = dev_malloc(&dev, total);
-    if (e == cudaSuccess) {
-        ds->allocations.push_back(dev);
-        ds->allocation_bytes.push_back(total);
-        ds->bytes += host_total;                                  // bytes that crossed the bus
-        e = cudaMemcpyAsync(dev, host, host_total, cudaMemcpyHostToDevice, 0);
-        if (e == cudaSuccess && nr) {
-            // one sphere per REFERENCE, in reference order: a cell's candidates become one contiguous read for k_traverse
-            k_spread_spheres<<<(unsigned)std::min<size_t>((nr + 255) / 256, (size_t)ds->sms * 32), 256, 0, 0>>>(
-                (const float4*)((char*)dev + off_spht), (const unsigned*)((char*)dev + off_refs), nr, (float4*)((char*)dev + off_sph));
-            e = cudaGetLastError();
-        }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(0);      // a staging block goes back to the pool on return
-    }
-    if (!keep_image) pinned_release(host);
-    if (e != cudaSuccess) return fail(RM_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(e));
-    d.tri = (const double*)((char*)dev + off_tri);
-    d.shd = (const double*)((char*)dev + off_shd);
-    d.sphr = (const float4*)((char*)dev + off_sph);
-    d.cells = (const uint2*)((char*)dev + off_cells);
-    d.occ = (const unsigned*)((char*)dev + off_occ);
-    d.refs = (const unsigned*)((char*)dev + off_refs);
-    *out = d;
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t workers = (nt + nc + nr < ((size_t)1 << 18)) ? 1 : std::min<size_t>(hw ? hw : 4, 8);
+    std::vector<std::thread> pool;
+    for (size_t w = 1; w < workers; w++)
+        pool.emplace_back([&, w] {
+            fill_triangles(nt * w / workers, nt * (w + 1) / workers);
+            fill_cells((nc * w / workers) & ~(size_t)31, w + 1 == workers ? nc : (nc * (w + 1) / workers) & ~(size_t)31);
+        });
+    fill_triangles(0, nt / workers);
+    fill_cells(0, workers == 1 ? nc : (nc / workers) & ~(size_t)31);
+    if (nr) memcpy(refs, g.references.data(), nr * sizeof(unsigned));
+    for (std::thread& t : pool) t.join();
+    if (keep_image) { g.image = host; g.image_bytes = host_total; Grid::g_grid_image_bytes += host_total; }
     return RM_OK;
 }
 
-static int build_device_scene(rm_device_scene* ds, const rm_scene* scene) {
+static void release_grid_image(GridImage& im) {
+    if (im.host && !im.cached) pinned_release(im.host);
+    im.host = nullptr;
+}
+
+static void point_grid(const GridImage& im, void* dev, DevGrid* out) {
+    DevGrid d = im.header;
+    d.tri = (const double*)((char*)dev + im.off_tri);
+    d.shd = (const double*)((char*)dev + im.off_shd);
+    d.sphr = (const float4*)((char*)dev + im.off_sph);
+    d.cells = (const uint2*)((char*)dev + im.off_cells);
+    d.occ = (const unsigned*)((char*)dev + im.off_occ);
+    d.refs = (const unsigned*)((char*)dev + im.off_refs);
+    *out = d;
+}
+
+// one sphere per REFERENCE, in reference order: a cell's candidates become one contiguous read for k_traverse
+static cudaError_t spread_spheres(const GridImage& im, void* dev, int sms, cudaStream_t stream) {
+    if (!im.nr) return cudaSuccess;
+    k_spread_spheres<<<(unsigned)std::min<size_t>((im.nr + 255) / 256, (size_t)sms * 32), 256, 0, stream>>>(
+        (const float4*)((char*)dev + im.off_spht), (const unsigned*)((char*)dev + im.off_refs), im.nr, (float4*)((char*)dev + im.off_sph));
+    return cudaGetLastError();
+}
+
+// One device allocation + one H2D copy per grid.
+static int upload_grid(rm_device_scene* ds, const Grid& g, DevGrid* out) {
+    GridImage im;
+    if (int st = prepare_grid_image(g, &im)) return st;
+    void* dev = nullptr;
+    cudaError_t e = dev_malloc(&dev, im.total);
+    if (e == cudaSuccess) {
+        ds->allocations.push_back(dev);
+        ds->allocation_bytes.push_back(im.total);
+        ds->bytes += im.host_total;                               // bytes that crossed the bus
+        e = cudaMemcpyAsync(dev, im.host, im.host_total, cudaMemcpyHostToDevice, 0);
+        if (e == cudaSuccess) e = spread_spheres(im, dev, ds->sms, 0);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(0);      // a staging block goes back to the pool on return
+    }
+    release_grid_image(im);
+    if (e != cudaSuccess) return fail(RM_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(e));
+    point_grid(im, dev, out);
+    return RM_OK;
+}
+
+// Object table of the device scene (analytic objects by value, grids by index); `place(grid, out)` puts one distinct grid on the device.
+template <class Place>
+static int build_scene_table(rm_device_scene* ds, const rm_scene* scene, Place place) {
     if (scene->objects.size() > (size_t)kMaxObjects)
         return fail(RM_ERR_UNSUPPORTED, "scene has more than " + std::to_string(kMaxObjects) + " objects");
-    RM_CUDA(cudaSetDevice(ds->device));
-    ds->sms = sm_count(ds->device);
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<false>, kTravBlock, 0) == cudaSuccess && occ > 0) ds->traverse_blocks_per_sm = occ;
-    cudaEvent_t e0, e1;
-    RM_CUDA(cudaEventCreate(&e0));
-    RM_CUDA(cudaEventCreate(&e1));
-    RM_CUDA(cudaEventRecord(e0, 0));
     std::map<const Grid*, int> grid_index;
     DevScene& s = ds->scene;
     s.n_objects = (int)scene->objects.size();
@@ -362,7 +440,7 @@ static int build_device_scene(rm_device_scene* ds, const rm_scene* scene) {
             auto it = grid_index.find(o.grid.get());
             if (it == grid_index.end()) {
                 if (s.n_grids >= kMaxGrids) return fail(RM_ERR_UNSUPPORTED, "scene has more than " + std::to_string(kMaxGrids) + " distinct grids");
-                if (int st = upload_grid(ds, *o.grid, &s.grid[s.n_grids])) return st;
+                if (int st = place(o.grid, &s.grid[s.n_grids])) return st;
                 ds->keep.push_back(o.grid);
                 it = grid_index.emplace(o.grid.get(), s.n_grids++).first;
             }
@@ -370,6 +448,23 @@ static int build_device_scene(rm_device_scene* ds, const rm_scene* scene) {
             ds->grid_objects.push_back((int)i);
         }
     }
+    return RM_OK;
+}
+
+static void device_scene_defaults(rm_device_scene* ds) {
+    ds->sms = sm_count(ds->device);
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<false>, kTravBlock, 0) == cudaSuccess && occ > 0) ds->traverse_blocks_per_sm = occ;
+}
+
+static int build_device_scene(rm_device_scene* ds, const rm_scene* scene) {
+    RM_CUDA(cudaSetDevice(ds->device));
+    device_scene_defaults(ds);
+    cudaEvent_t e0, e1;
+    RM_CUDA(cudaEventCreate(&e0));
+    RM_CUDA(cudaEventCreate(&e1));
+    RM_CUDA(cudaEventRecord(e0, 0));
+    if (int st = build_scene_table(ds, scene, [&](const std::shared_ptr<Grid>& g, DevGrid* out) { return upload_grid(ds, *g, out); })) return st;
     RM_CUDA(cudaEventRecord(e1, 0));
     RM_CUDA(cudaEventSynchronize(e1));
     float ms = 0.f;
@@ -379,6 +474,154 @@ static int build_device_scene(rm_device_scene* ds, const rm_scene* scene) {
     cudaEventDestroy(e1);
     return RM_OK;
 }
+
+}  // namespace rm
+
+// --------------------------------------------------------------------- a scene on several devices at once
+//
+// rm_render_tiled with several shares: instead of one full upload followed by device-to-device clones, the host image of every
+// grid crosses the bus ONCE, in slices — share g copies slice g to its own device over its own PCIe link — and every share then
+// pulls the other slices from its peers over NVLink (an all-gather of the image); the per-reference spheres are spread on
+// every device locally.  One host thread per share calls rm_scene_group_join; all of them must.
+struct rm_scene_group {
+    const rm_scene* scene = nullptr;
+    std::vector<int> devices;
+    std::vector<std::shared_ptr<Grid>> grids;       // distinct grids, in DevScene::grid order
+    std::vector<GridImage> images;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<std::vector<void*>> blocks;         // [share][grid]: the share's device block
+    std::vector<cudaEvent_t> uploaded;              // [share]: its slice of every grid is on its device
+    int arrived[2] = {0, 0};                        // shares that reached barrier 0 (slices uploaded) / 1 (gather done)
+    bool failed = false;
+
+    // every share arrives exactly once per barrier, also after a failure of its own (so nobody waits forever)
+    bool barrier(int which, bool ok) {
+        std::unique_lock<std::mutex> lk(mu);
+        if (!ok) failed = true;
+        arrived[which]++;
+        cv.notify_all();
+        cv.wait(lk, [&] { return arrived[which] >= (int)devices.size(); });
+        return !failed;
+    }
+    ~rm_scene_group() {
+        for (GridImage& im : images) release_grid_image(im);
+        for (cudaEvent_t e : uploaded) if (e) cudaEventDestroy(e);
+    }
+};
+
+extern "C" {
+
+rm_scene_group* rm_scene_group_create(const rm_scene* scene, const int32_t* devices, int count) {
+    if (!scene || !devices || count <= 0) { fail(RM_ERR_INVALID_ARGUMENT, "rm_scene_group_create: bad argument"); return nullptr; }
+    int visible = 0;
+    cudaError_t e = cudaGetDeviceCount(&visible);
+    for (int g = 0; g < count; g++)
+        if (e != cudaSuccess || devices[g] < 0 || devices[g] >= visible) {
+            fail(RM_ERR_CUDA, std::string("no usable CUDA device ") + std::to_string(devices[g]) + " (" + (e != cudaSuccess ? cudaGetErrorString(e) : "ordinal out of range") +
+                                  "); this library has no CPU path");
+            return nullptr;
+        }
+    rm_scene_group* grp = new rm_scene_group();
+    grp->scene = scene;
+    grp->devices.assign(devices, devices + count);
+    grp->blocks.assign((size_t)count, {});
+    grp->uploaded.assign((size_t)count, nullptr);
+    // the host images of the distinct grids, in the order build_scene_table meets them (flattened once per immutable grid, cached with it)
+    for (const Object& o : scene->objects) {
+        if (o.geometry != GEOM_GRID) continue;
+        bool seen = false;
+        for (const std::shared_ptr<Grid>& g : grp->grids) seen = seen || g.get() == o.grid.get();
+        if (seen) continue;
+        GridImage im;
+        if (prepare_grid_image(*o.grid, &im) != RM_OK) { delete grp; return nullptr; }
+        grp->grids.push_back(o.grid);
+        grp->images.push_back(im);
+    }
+    return grp;
+}
+
+rm_device_scene* rm_scene_group_join(rm_scene_group* grp, int share) {
+    if (!grp || share < 0 || share >= (int)grp->devices.size()) { fail(RM_ERR_INVALID_ARGUMENT, "rm_scene_group_join: bad argument"); return nullptr; }
+    const int G = (int)grp->devices.size();
+    const int device = grp->devices[(size_t)share];
+    rm_device_scene* ds = new rm_device_scene();
+    ds->device = device;
+    std::vector<void*>& mine = grp->blocks[(size_t)share];
+    auto slice = [&](const GridImage& im, int j, size_t* begin, size_t* end) {
+        *begin = (im.host_total * (size_t)j / (size_t)G) & ~(size_t)255;
+        *end = j + 1 == G ? im.host_total : (im.host_total * (size_t)(j + 1) / (size_t)G) & ~(size_t)255;
+    };
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) { device_scene_defaults(ds); e = cudaEventCreate(&e0); }
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    if (e == cudaSuccess) e = cudaEventRecord(e0, 0);
+    // phase 1: my slice of every image, host -> my device
+    for (size_t i = 0; i < grp->images.size() && e == cudaSuccess; i++) {
+        const GridImage& im = grp->images[i];
+        void* dev = nullptr;
+        e = dev_malloc(&dev, im.total);
+        if (e != cudaSuccess) break;
+        mine.push_back(dev);
+        ds->allocations.push_back(dev);
+        ds->allocation_bytes.push_back(im.total);
+        size_t b, en;
+        slice(im, share, &b, &en);
+        if (en > b) e = cudaMemcpyAsync((char*)dev + b, im.host + b, en - b, cudaMemcpyHostToDevice, 0);
+        ds->bytes += en - b;                                      // bytes that crossed the bus for this share
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&grp->uploaded[(size_t)share], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(grp->uploaded[(size_t)share], 0);
+    bool ok = grp->barrier(0, e == cudaSuccess);
+    // phase 2: the other slices from the peers that hold them (NVLink), then the per-reference spheres
+    if (ok) {
+        for (size_t i = 0; i < grp->images.size() && e == cudaSuccess; i++) {
+            const GridImage& im = grp->images[i];
+            for (int step = 1; step < G && e == cudaSuccess; step++) {
+                const int j = (share + step) % G;                 // every share starts with a different peer
+                size_t b, en;
+                slice(im, j, &b, &en);
+                if (en <= b) continue;
+                e = cudaStreamWaitEvent(0, grp->uploaded[(size_t)j], 0);
+                if (e == cudaSuccess)
+                    e = cudaMemcpyPeerAsync((char*)mine[i] + b, device, (const char*)grp->blocks[(size_t)j][i] + b, grp->devices[(size_t)j], en - b, 0);
+            }
+            if (e == cudaSuccess) e = spread_spheres(im, mine[i], ds->sms, 0);
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(e1, 0);
+        if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    }
+    // nobody frees a block a peer may still be reading
+    ok = grp->barrier(1, ok && e == cudaSuccess);
+    int st = RM_OK;
+    if (ok) {
+        size_t next = 0;
+        st = build_scene_table(ds, grp->scene, [&](const std::shared_ptr<Grid>&, DevGrid* out) {
+            point_grid(grp->images[next], mine[next], out);
+            next++;
+            return (int)RM_OK;
+        });
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        ds->upload_ms = ms;
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (!ok || st != RM_OK) {
+        if (e != cudaSuccess) fail(RM_ERR_CUDA, std::string("scene upload (share ") + std::to_string(share) + "): " + cudaGetErrorString(e));
+        else if (st == RM_OK) fail(RM_ERR_CUDA, "scene upload failed on another device of the group");
+        delete ds;
+        return nullptr;
+    }
+    return ds;
+}
+
+void rm_scene_group_destroy(rm_scene_group* grp) { delete grp; }
+
+}  // extern "C"
+
+namespace rm {
 
 // Observer of the launches of one Scene::intersect pass (stage timing / launch counting).
 struct LaunchHook {
@@ -449,12 +692,15 @@ struct rm_renderer {
     Queue q[2]{};
     double* queue_mem = nullptr;
     unsigned* id_mem = nullptr;
+    std::shared_ptr<rm::PixelMap> pixel_map_ref;      // shared with the other renderers of the same frame layout on this device
     unsigned* pixel_map = nullptr;
+    size_t uploaded_pixel_map_bytes = 0;
     unsigned* counters = nullptr;
     size_t counter_slots = 0;
     IntersectBuffers isect;
     double* accum = nullptr;
     bool owns_accum = false;
+    size_t accum_bytes = 0;
     DevTotals* totals = nullptr;
     size_t batch_spp = 1;
     uint64_t launches = 0;
@@ -475,9 +721,9 @@ struct rm_renderer {
         for (auto& e : event_pool) cudaEventDestroy(e);
         if (ev_rendered) cudaEventDestroy(ev_rendered);
         if (ev_reduced) cudaEventDestroy(ev_reduced);
-        dev_free(queue_mem); dev_free(id_mem); dev_free(pixel_map); dev_free(rp.contrib); dev_free(counters); dev_free(totals);
+        dev_free(queue_mem); dev_free(id_mem); dev_free(rp.contrib); dev_free(counters); dev_free(totals);
         isect.release();
-        if (owns_accum) dev_free(accum);
+        if (owns_accum) accum_release(device, accum_bytes, accum);
         if (owns_stream && stream) cudaStreamDestroy(stream);
         if (owns_scene) delete ds;
     }
@@ -506,6 +752,58 @@ static std::vector<unsigned> build_pixel_map(const rm_settings& s, const rm_gpu_
     return map;
 }
 
+// The launch order of a share's pixels depends only on the frame, the tile size and the share: it is built on the host and
+// uploaded once per (device, frame, tiles, partition, rank, world) and shared by every renderer that needs it afterwards —
+// render_tiled makes a renderer per frame, and 8 MB of indices per 1080p share were 5-8 ms of every frame's start.
+namespace {
+struct PixelMapKey {
+    int device; size_t W, H, tw, th; unsigned partition; int rank, world;
+    bool operator<(const PixelMapKey& o) const {
+        return std::tie(device, W, H, tw, th, partition, rank, world) < std::tie(o.device, o.W, o.H, o.tw, o.th, o.partition, o.rank, o.world);
+    }
+};
+std::mutex g_pixel_map_mu;
+// never destroyed: its entries free device memory, which must not happen from a static destructor after the CUDA runtime is gone
+std::map<PixelMapKey, std::shared_ptr<PixelMap>>& g_pixel_maps = *new std::map<PixelMapKey, std::shared_ptr<PixelMap>>();
+constexpr size_t kPixelMapCacheBytes = (size_t)512 << 20;
+}  // namespace
+
+PixelMap::~PixelMap() {
+    if (dev) { cudaSetDevice(device); dev_free(dev); }
+}
+
+static void pixel_map_cache_trim(size_t keep_bytes) {      // g_pixel_map_mu held
+    size_t bytes = 0;
+    for (auto& kv : g_pixel_maps) bytes += kv.second->n * sizeof(unsigned);
+    for (auto it = g_pixel_maps.begin(); it != g_pixel_maps.end() && bytes > keep_bytes;) {
+        if (it->second.use_count() == 1) { bytes -= it->second->n * sizeof(unsigned); it = g_pixel_maps.erase(it); }
+        else ++it;
+    }
+}
+
+static int pixel_map_for(rm_renderer* r) {
+    const rm_settings& s = r->settings;
+    const int world = r->opt.world_size > 1 ? r->opt.world_size : 1;
+    const bool tiles = r->opt.partition == RM_PARTITION_TILES && world > 1;
+    const PixelMapKey key{r->device, s.camera_settings.backbuffer_width, s.camera_settings.backbuffer_height, s.tile_size[0], s.tile_size[1],
+                          tiles ? 1u : 0u, tiles ? r->opt.rank : 0, tiles ? world : 1};
+    std::lock_guard<std::mutex> lk(g_pixel_map_mu);       // also serialises the build of a missing map between the shares of a task
+    auto it = g_pixel_maps.find(key);
+    if (it != g_pixel_maps.end()) { r->pixel_map_ref = it->second; return RM_OK; }
+    std::vector<unsigned> map = build_pixel_map(s, r->opt);
+    auto pm = std::make_shared<PixelMap>();
+    pm->device = r->device;
+    pm->n = map.size();
+    RM_CUDA(dev_malloc(&pm->dev, std::max<size_t>(pm->n, 1) * sizeof(unsigned)));
+    if (pm->n) RM_CUDA(cudaMemcpyAsync(pm->dev, map.data(), pm->n * sizeof(unsigned), cudaMemcpyHostToDevice, r->stream));
+    RM_CUDA(cudaStreamSynchronize(r->stream));
+    r->uploaded_pixel_map_bytes = pm->n * sizeof(unsigned);
+    pixel_map_cache_trim(kPixelMapCacheBytes);
+    g_pixel_maps[key] = pm;
+    r->pixel_map_ref = pm;
+    return RM_OK;
+}
+
 static int renderer_init(rm_renderer* r) {
     const rm_settings& s = r->settings;
     const size_t W = s.camera_settings.backbuffer_width, H = s.camera_settings.backbuffer_height;
@@ -518,11 +816,9 @@ static int renderer_init(rm_renderer* r) {
     if (r->opt.stream) r->stream = (cudaStream_t)r->opt.stream;
     else { RM_CUDA(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking)); r->owns_stream = true; }
 
-    std::vector<unsigned> map = build_pixel_map(s, r->opt);
-    const size_t npix = map.size();
-    RM_CUDA(dev_malloc(&r->pixel_map, std::max<size_t>(npix, 1) * sizeof(unsigned)));
-    if (npix) RM_CUDA(cudaMemcpyAsync(r->pixel_map, map.data(), npix * sizeof(unsigned), cudaMemcpyHostToDevice, r->stream));
-    RM_CUDA(cudaStreamSynchronize(r->stream));
+    if (int st = pixel_map_for(r)) return st;
+    const size_t npix = r->pixel_map_ref->n;
+    r->pixel_map = r->pixel_map_ref->dev;
 
     // batch: enough paths in flight to fill the machine many times over, bounded in memory
     size_t spp = r->opt.batch_spp;
@@ -569,7 +865,11 @@ static int renderer_init(rm_renderer* r) {
     rp.totals = r->totals;
     RM_CUDA(cudaMemsetAsync(r->totals, 0, sizeof(DevTotals), r->stream));
     if (r->opt.accum_device) r->accum = (double*)r->opt.accum_device;
-    else { RM_CUDA(dev_malloc(&r->accum, W * H * 3 * sizeof(double))); r->owns_accum = true; }
+    else {      // not from the pool: peers read it in place
+        r->accum_bytes = std::max<size_t>(W * H, 1) * 3 * sizeof(double);
+        RM_CUDA(accum_acquire(r->device, r->accum_bytes, &r->accum));
+        r->owns_accum = true;
+    }
     RM_CUDA(cudaMemsetAsync(r->accum, 0, W * H * 3 * sizeof(double), r->stream));
     return RM_OK;
 }
@@ -717,11 +1017,17 @@ int reduce_accumulators_to_host(rm_renderer* const* rs, int count, rm_vec3* out,
     if (!out_is_pinned || count > kMaxShares) return reduce_gather_to_host(rs, count, out);
     for (int g = 0; g < count; g++)
         for (int j = 0; j < count; j++) {
-            int can = 1;
-            if (rs[g]->device != rs[j]->device && (cudaDeviceCanAccessPeer(&can, rs[g]->device, rs[j]->device) != cudaSuccess || !can)) {
+            if (rs[g]->device == rs[j]->device) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, rs[g]->device, rs[j]->device) != cudaSuccess || !can) {
                 cudaGetLastError();
                 return reduce_gather_to_host(rs, count, out);       // no peer mapping between these two devices: staged copies
             }
+            // device g reads device j's accumulator in place (a no-op after the first time)
+            RM_CUDA(cudaSetDevice(rs[g]->device));
+            const cudaError_t pe = cudaDeviceEnablePeerAccess(rs[j]->device, 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return reduce_gather_to_host(rs, count, out); }
+            cudaGetLastError();
         }
     // the frame as the devices see it (the same address under unified addressing)
     double *out_dev = nullptr, *mean_dev = nullptr;
@@ -817,66 +1123,6 @@ rm_device_scene* rm_device_scene_create(const rm_scene* scene, int device) {
 }
 
 void rm_device_scene_destroy(rm_device_scene* ds) { delete ds; }
-
-/* The same scene on another device of this process: the grid blocks are copied device to device (NVLink peer copy)
- * instead of being flattened, staged and uploaded from the host again. */
-rm_device_scene* rm_device_scene_clone_to(const rm_device_scene* src, int device) {
-    if (!src) { fail(RM_ERR_INVALID_ARGUMENT, "rm_device_scene_clone_to: null scene"); return nullptr; }
-    int count = 0;
-    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
-        cudaGetLastError();
-        fail(RM_ERR_CUDA, "no usable CUDA device " + std::to_string(device) + "; this library has no CPU path");
-        return nullptr;
-    }
-    rm_device_scene* ds = new rm_device_scene();
-    ds->device = device;
-    ds->scene = src->scene;
-    ds->grid_objects = src->grid_objects;
-    ds->keep = src->keep;
-    cudaError_t e = cudaSetDevice(device);
-    ds->sms = sm_count(device);
-    ds->traverse_blocks_per_sm = src->traverse_blocks_per_sm;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (e == cudaSuccess) e = cudaEventCreate(&e0);
-    if (e == cudaSuccess) e = cudaEventCreate(&e1);
-    if (e == cudaSuccess) e = cudaEventRecord(e0, 0);
-    for (size_t i = 0; i < src->allocations.size() && e == cudaSuccess; i++) {
-        void* dev = nullptr;
-        e = dev_malloc(&dev, src->allocation_bytes[i]);
-        if (e != cudaSuccess) break;
-        ds->allocations.push_back(dev);
-        ds->allocation_bytes.push_back(src->allocation_bytes[i]);
-        ds->bytes += src->allocation_bytes[i];
-        cudaDeviceEnablePeerAccess(src->device, 0);
-        cudaGetLastError();
-        e = cudaMemcpyPeerAsync(dev, device, src->allocations[i], src->device, src->allocation_bytes[i], 0);
-        // the block keeps its layout: every array pointer moves by the same distance
-        const ptrdiff_t shift = (const char*)dev - (const char*)src->allocations[i];
-        DevGrid& g = ds->scene.grid[i];
-        auto move = [&](auto*& p) { p = (std::remove_reference_t<decltype(p)>)((const char*)p + shift); };
-        move(g.cells); move(g.occ); move(g.refs); move(g.tri); move(g.sphr); move(g.shd);
-    }
-    if (e == cudaSuccess) e = cudaEventRecord(e1, 0);
-    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
-    float ms = 0.f;
-    if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
-    ds->upload_ms = ms;
-    if (e0) cudaEventDestroy(e0);
-    if (e1) cudaEventDestroy(e1);
-    if (e != cudaSuccess) {
-        fail(RM_ERR_CUDA, std::string("rm_device_scene_clone_to: ") + cudaGetErrorString(e));
-        delete ds;
-        return nullptr;
-    }
-    return ds;
-}
-
-/* Renderer that takes ownership of `ds` (destroys it with the renderer). */
-rm_renderer* rm_renderer_create_owning(rm_device_scene* ds, const rm_settings* settings, const rm_gpu_options* options) {
-    rm_renderer* r = rm_renderer_create_on(ds, settings, options);
-    if (r) r->owns_scene = true;
-    return r;
-}
 
 rm_device_scene* rm_renderer_device_scene(rm_renderer* r) { return r ? r->ds : nullptr; }
 
@@ -1118,7 +1364,7 @@ int rm_renderer_stats(rm_renderer* r, rm_stats* out) {
     out->kernel_launches = r->launches;
     out->device_ms = r->device_ms;
     out->upload_ms = r->ds ? r->ds->upload_ms : 0.0;
-    out->upload_bytes = (r->ds ? r->ds->bytes : 0) + (uint64_t)r->rp.n_pixels * sizeof(unsigned);
+    out->upload_bytes = (r->ds ? r->ds->bytes : 0) + (uint64_t)r->uploaded_pixel_map_bytes;
     return RM_OK;
 }
 
@@ -1188,7 +1434,15 @@ int rm_measure_fp64_rate(int device, double* gops_out) {
 
 /* Hand the cached device memory (stream-ordered pool of every visible device) and the cached pinned staging blocks back. */
 int rm_release_cached_memory(void) {
+    {
+        std::lock_guard<std::mutex> lk(g_pixel_map_mu);
+        pixel_map_cache_trim(0);
+    }
     int count = 0;
+    int before = 0;
+    cudaGetDevice(&before);
+    accum_cache_clear();
+    cudaSetDevice(before);
     if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); count = 0; }
     int current = 0;
     if (count) cudaGetDevice(&current);

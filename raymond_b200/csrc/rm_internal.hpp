@@ -109,9 +109,13 @@ struct Trace {
 
 // internal entry points of rm_device.cu used by the multi-GPU task driver (C linkage, not part of include/raymond.h)
 extern "C" {
-rm_device_scene* rm_device_scene_clone_to(const rm_device_scene* src, int device);
-rm_renderer* rm_renderer_create_owning(rm_device_scene* ds, const rm_settings* settings, const rm_gpu_options* options);
 rm_renderer* rm_renderer_create_unbound(const rm_settings* settings, const rm_gpu_options* options);
+// a scene placed on several devices at once (slices over every device's PCIe link + an all-gather over NVLink): one host thread
+// per share calls _join, ALL shares must; _join returns the share's device scene or NULL
+struct rm_scene_group;
+rm_scene_group* rm_scene_group_create(const rm_scene* scene, const int32_t* devices, int count);
+rm_device_scene* rm_scene_group_join(rm_scene_group* group, int share);
+void rm_scene_group_destroy(rm_scene_group* group);
 int rm_renderer_bind_scene(rm_renderer* r, rm_device_scene* ds, int owning);
 rm_device_scene* rm_renderer_device_scene(rm_renderer* r);
 }

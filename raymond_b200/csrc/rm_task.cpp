@@ -222,34 +222,29 @@ rm_task* rm_render_tiled(const rm_scene* scene, const rm_settings* settings, con
         o.device_count = 0;
         return o;
     };
-    std::mutex first_mu;
-    std::condition_variable first_cv;
-    rm_device_scene* first = nullptr;
-    bool first_ready = false;
+    // several shares: the scene image crosses the bus once, in slices, and is gathered over NVLink (rm_scene_group)
+    rm_scene_group* group = nullptr;
+    if (G > 1) {
+        group = rm_scene_group_create(scene, devices.data(), (int)G);
+        if (!group) { delete t; return nullptr; }
+    }
     auto record = [&](size_t g) { status[g] = rm_last_status(); errors[g] = rm_last_error(); };
     auto create = [&](size_t g) {
         rm_gpu_options o = options_for(g);
-        if (g == 0) {
+        if (!group) {
             t->renderers[0] = rm_renderer_create(scene, settings, &o);
             if (!t->renderers[0]) record(0);
-            std::lock_guard<std::mutex> lk(first_mu);
-            first = t->renderers[0] ? rm_renderer_device_scene(t->renderers[0]) : nullptr;
-            first_ready = true;
-            first_cv.notify_all();
             return;
         }
         rm_renderer* r = rm_renderer_create_unbound(settings, &o);
         if (!r) record(g);
-        {
-            std::unique_lock<std::mutex> lk(first_mu);
-            first_cv.wait(lk, [&] { return first_ready; });
-        }
-        if (r && first) {
-            rm_device_scene* ds = rm_device_scene_clone_to(first, o.device);
-            if (ds) rm_renderer_bind_scene(r, ds, 1);
-            else { record(g); rm_renderer_destroy(r); r = nullptr; }
-        } else if (r) {
-            rm_renderer_destroy(r);
+        rm_device_scene* ds = rm_scene_group_join(group, (int)g);      // every share joins, whatever happened to its renderer
+        if (!ds && r) record(g);
+        if (r && ds) {
+            rm_renderer_bind_scene(r, ds, 1);
+        } else {
+            if (r) rm_renderer_destroy(r);
+            if (ds) rm_device_scene_destroy(ds);
             r = nullptr;
         }
         t->renderers[g] = r;
@@ -260,11 +255,16 @@ rm_task* rm_render_tiled(const rm_scene* scene, const rm_settings* settings, con
         create(0);
         for (std::thread& th : pool) th.join();
     }
+    if (group) rm_scene_group_destroy(group);
     trace.mark("rm_render_tiled: scene resident and renderers ready on every device");
     for (size_t g = 0; g < G; g++)
-        if (!t->renderers[g] && (g == 0 || t->renderers[0])) {
+        if (!t->renderers[g]) {
+            // report the first share that has an error of its own (a share whose peers failed only knows "another device failed")
+            size_t bad = g;
+            for (size_t k = 0; k < G; k++)
+                if (!t->renderers[k] && status[k] != RM_OK && errors[k].find("another device") == std::string::npos) { bad = k; break; }
             for (rm_renderer* r : t->renderers) rm_renderer_destroy(r);
-            fail(status[g] ? status[g] : RM_ERR_CUDA, errors[g]);
+            fail(status[bad] ? status[bad] : RM_ERR_CUDA, errors[bad]);
             delete t;
             return nullptr;
         }
