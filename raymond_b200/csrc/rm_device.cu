@@ -92,43 +92,66 @@ static void dev_free(void* p) { if (p) cudaFreeAsync(p, 0); }
 int dev_alloc(void** p, size_t bytes) { return (int)dev_malloc_raw(p, bytes); }
 void dev_release(void* p) { dev_free(p); }
 
-// ---- accumulators: plain cudaMalloc blocks (peers read them in place through cudaDeviceEnablePeerAccess), kept per device for the
-// next renderer — with peer access on, cudaMalloc / cudaFree of 50 MB map and unmap on every peer and cost milliseconds
+// ---- peer-visible blocks: what other devices of the process read in place — the accumulators (the exchange kernel of a
+// multi-device task) and the scene blocks (the all-gather of a scene placed on several devices) — are plain cudaMalloc
+// allocations, reachable through cudaDeviceEnablePeerAccess, and are kept per (device, size) for the next frame: with peer
+// access on, cudaMalloc / cudaFree map and unmap on every peer and cost milliseconds.
 namespace {
-struct AccumBlock { int device; size_t bytes; void* p; };
-std::mutex g_accum_mu;
-std::vector<AccumBlock>& g_accum_free = *new std::vector<AccumBlock>();      // never destroyed (frees device memory)
-constexpr size_t kAccumCacheBytes = (size_t)2 << 30;
+struct VisibleBlock { int device; size_t bytes; void* p; };
+std::mutex g_visible_mu;
+std::vector<VisibleBlock>& g_visible_free = *new std::vector<VisibleBlock>();      // never destroyed (it frees device memory)
+constexpr size_t kVisibleCacheBytes = (size_t)16 << 30;
 }  // namespace
 
-static cudaError_t accum_acquire(int device, size_t bytes, double** out) {
+static cudaError_t visible_acquire(int device, size_t bytes, void** out) {
     {
-        std::lock_guard<std::mutex> lk(g_accum_mu);
-        for (size_t i = 0; i < g_accum_free.size(); i++)
-            if (g_accum_free[i].device == device && g_accum_free[i].bytes == bytes) {
-                *out = (double*)g_accum_free[i].p;
-                g_accum_free.erase(g_accum_free.begin() + (long)i);
+        std::lock_guard<std::mutex> lk(g_visible_mu);
+        for (size_t i = 0; i < g_visible_free.size(); i++)
+            if (g_visible_free[i].device == device && g_visible_free[i].bytes == bytes) {
+                *out = g_visible_free[i].p;
+                g_visible_free.erase(g_visible_free.begin() + (long)i);
                 return cudaSuccess;
             }
     }
-    return cudaMalloc(out, bytes);
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation) {          // make room: drop what is cached, then once more
+        cudaGetLastError();
+        std::vector<VisibleBlock> drop;
+        { std::lock_guard<std::mutex> lk(g_visible_mu); drop.swap(g_visible_free); }
+        for (const VisibleBlock& b : drop) { cudaSetDevice(b.device); cudaFree(b.p); }
+        cudaSetDevice(device);
+        e = cudaMalloc(out, bytes);
+    }
+    return e;
 }
 
-static void accum_release(int device, size_t bytes, void* p) {
+static void visible_release(int device, size_t bytes, void* p) {      // the caller's work on `p` is complete
     if (!p) return;
     {
-        std::lock_guard<std::mutex> lk(g_accum_mu);
+        std::lock_guard<std::mutex> lk(g_visible_mu);
         size_t cached = 0;
-        for (const AccumBlock& b : g_accum_free) cached += b.bytes;
-        if (cached + bytes <= kAccumCacheBytes) { g_accum_free.push_back({device, bytes, p}); return; }
+        for (const VisibleBlock& b : g_visible_free) cached += b.bytes;
+        if (cached + bytes <= kVisibleCacheBytes) { g_visible_free.push_back({device, bytes, p}); return; }
     }
+    cudaSetDevice(device);
     cudaFree(p);
 }
 
-static void accum_cache_clear() {
-    std::lock_guard<std::mutex> lk(g_accum_mu);
-    for (const AccumBlock& b : g_accum_free) { cudaSetDevice(b.device); cudaFree(b.p); }
-    g_accum_free.clear();
+static void visible_cache_clear() {
+    std::vector<VisibleBlock> drop;
+    { std::lock_guard<std::mutex> lk(g_visible_mu); drop.swap(g_visible_free); }
+    for (const VisibleBlock& b : drop) { cudaSetDevice(b.device); cudaFree(b.p); }
+}
+
+// device `from` may read the memory of device `to` in place (a no-op after the first time; false when the hardware cannot)
+static bool enable_peer(int from, int to) {
+    if (from == to) return true;
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, from, to) != cudaSuccess || !can) { cudaGetLastError(); return false; }
+    if (cudaSetDevice(from) != cudaSuccess) { cudaGetLastError(); return false; }
+    const cudaError_t e = cudaDeviceEnablePeerAccess(to, 0);
+    cudaGetLastError();
+    return e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled;
 }
 
 // ---- pinned staging pool
@@ -246,7 +269,7 @@ struct rm_device_scene {
         cudaSetDevice(device);
         cudaDeviceSynchronize();            // queries may still be running on the caller's streams
         if (query_done) cudaEventDestroy(query_done);
-        for (void* p : allocations) dev_free(p);
+        for (size_t i = 0; i < allocations.size(); i++) visible_release(device, allocation_bytes[i], allocations[i]);
         query.release();
         dev_free(query_counters);
     }
@@ -401,7 +424,7 @@ static int upload_grid(rm_device_scene* ds, const Grid& g, DevGrid* out) {
     GridImage im;
     if (int st = prepare_grid_image(g, &im)) return st;
     void* dev = nullptr;
-    cudaError_t e = dev_malloc(&dev, im.total);
+    cudaError_t e = visible_acquire(ds->device, im.total, &dev);
     if (e == cudaSuccess) {
         ds->allocations.push_back(dev);
         ds->allocation_bytes.push_back(im.total);
@@ -553,6 +576,7 @@ rm_device_scene* rm_scene_group_join(rm_scene_group* grp, int share) {
         *end = j + 1 == G ? im.host_total : (im.host_total * (size_t)(j + 1) / (size_t)G) & ~(size_t)255;
     };
     cudaEvent_t e0 = nullptr, e1 = nullptr;
+    for (int j = 0; j < G; j++) enable_peer(device, grp->devices[(size_t)j]);      // direct NVLink copies where the hardware has them
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) { device_scene_defaults(ds); e = cudaEventCreate(&e0); }
     if (e == cudaSuccess) e = cudaEventCreate(&e1);
@@ -561,7 +585,7 @@ rm_device_scene* rm_scene_group_join(rm_scene_group* grp, int share) {
     for (size_t i = 0; i < grp->images.size() && e == cudaSuccess; i++) {
         const GridImage& im = grp->images[i];
         void* dev = nullptr;
-        e = dev_malloc(&dev, im.total);
+        e = visible_acquire(device, im.total, &dev);
         if (e != cudaSuccess) break;
         mine.push_back(dev);
         ds->allocations.push_back(dev);
@@ -723,7 +747,7 @@ struct rm_renderer {
         if (ev_reduced) cudaEventDestroy(ev_reduced);
         dev_free(queue_mem); dev_free(id_mem); dev_free(rp.contrib); dev_free(counters); dev_free(totals);
         isect.release();
-        if (owns_accum) accum_release(device, accum_bytes, accum);
+        if (owns_accum) visible_release(device, accum_bytes, accum);
         if (owns_stream && stream) cudaStreamDestroy(stream);
         if (owns_scene) delete ds;
     }
@@ -816,9 +840,11 @@ static int renderer_init(rm_renderer* r) {
     if (r->opt.stream) r->stream = (cudaStream_t)r->opt.stream;
     else { RM_CUDA(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking)); r->owns_stream = true; }
 
+    Trace trace;
     if (int st = pixel_map_for(r)) return st;
     const size_t npix = r->pixel_map_ref->n;
     r->pixel_map = r->pixel_map_ref->dev;
+    trace.mark("renderer_init: stream + pixel map");
 
     // batch: enough paths in flight to fill the machine many times over, bounded in memory
     size_t spp = r->opt.batch_spp;
@@ -829,6 +855,7 @@ static int renderer_init(rm_renderer* r) {
         size_t target = (size_t)64 << 20;
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) target = std::min(target, std::max<size_t>(free_b / 4 / 328, (size_t)1 << 20));
+        trace.mark("renderer_init: cudaMemGetInfo");
         spp = npix ? std::max<size_t>(1, target / npix) : 1;
         spp = std::min<size_t>(spp, 64);
         // ... and never more than this share of the job renders (a rank / device of a sample-split job gets 1 / world_size of them)
@@ -867,10 +894,11 @@ static int renderer_init(rm_renderer* r) {
     if (r->opt.accum_device) r->accum = (double*)r->opt.accum_device;
     else {      // not from the pool: peers read it in place
         r->accum_bytes = std::max<size_t>(W * H, 1) * 3 * sizeof(double);
-        RM_CUDA(accum_acquire(r->device, r->accum_bytes, &r->accum));
+        RM_CUDA(visible_acquire(r->device, r->accum_bytes, (void**)&r->accum));
         r->owns_accum = true;
     }
     RM_CUDA(cudaMemsetAsync(r->accum, 0, W * H * 3 * sizeof(double), r->stream));
+    trace.mark("renderer_init: queues, counters, accumulator allocated");
     return RM_OK;
 }
 
@@ -1017,17 +1045,7 @@ int reduce_accumulators_to_host(rm_renderer* const* rs, int count, rm_vec3* out,
     if (!out_is_pinned || count > kMaxShares) return reduce_gather_to_host(rs, count, out);
     for (int g = 0; g < count; g++)
         for (int j = 0; j < count; j++) {
-            if (rs[g]->device == rs[j]->device) continue;
-            int can = 0;
-            if (cudaDeviceCanAccessPeer(&can, rs[g]->device, rs[j]->device) != cudaSuccess || !can) {
-                cudaGetLastError();
-                return reduce_gather_to_host(rs, count, out);       // no peer mapping between these two devices: staged copies
-            }
-            // device g reads device j's accumulator in place (a no-op after the first time)
-            RM_CUDA(cudaSetDevice(rs[g]->device));
-            const cudaError_t pe = cudaDeviceEnablePeerAccess(rs[j]->device, 0);
-            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return reduce_gather_to_host(rs, count, out); }
-            cudaGetLastError();
+            if (!enable_peer(rs[g]->device, rs[j]->device)) return reduce_gather_to_host(rs, count, out);   // no peer mapping: staged copies
         }
     // the frame as the devices see it (the same address under unified addressing)
     double *out_dev = nullptr, *mean_dev = nullptr;
@@ -1441,7 +1459,7 @@ int rm_release_cached_memory(void) {
     int count = 0;
     int before = 0;
     cudaGetDevice(&before);
-    accum_cache_clear();
+    visible_cache_clear();
     cudaSetDevice(before);
     if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); count = 0; }
     int current = 0;

@@ -227,6 +227,7 @@ rm_task* rm_render_tiled(const rm_scene* scene, const rm_settings* settings, con
     if (G > 1) {
         group = rm_scene_group_create(scene, devices.data(), (int)G);
         if (!group) { delete t; return nullptr; }
+        trace.mark("rm_render_tiled: host images of the grids ready");
     }
     auto record = [&](size_t g) { status[g] = rm_last_status(); errors[g] = rm_last_error(); };
     auto create = [&](size_t g) {
@@ -236,9 +237,12 @@ rm_task* rm_render_tiled(const rm_scene* scene, const rm_settings* settings, con
             if (!t->renderers[0]) record(0);
             return;
         }
+        Trace share_trace;
         rm_renderer* r = rm_renderer_create_unbound(settings, &o);
         if (!r) record(g);
+        if (share_trace.on) share_trace.mark(("share " + std::to_string(g) + ": renderer (stream, pixel map, queues, accumulator) ready").c_str());
         rm_device_scene* ds = rm_scene_group_join(group, (int)g);      // every share joins, whatever happened to its renderer
+        if (share_trace.on) share_trace.mark(("share " + std::to_string(g) + ": scene slice uploaded, peers' slices gathered").c_str());
         if (!ds && r) record(g);
         if (r && ds) {
             rm_renderer_bind_scene(r, ds, 1);
