@@ -572,10 +572,15 @@ class TaskHandle:
         lib().rm_tile_free(C.byref(m.tile))
         return msg
 
-    def await_(self) -> np.ndarray:
-        """r#await(): block, then the averaged frame as (H, W, 3) f64 (row-major W*H Vec<Vector3>)."""
+    def await_(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """r#await(): block, then the averaged frame as (H, W, 3) f64 (row-major W*H Vec<Vector3>).  `out` = a C-contiguous f64
+        array of that shape to write into (a caller rendering frame after frame keeps one, as the C ABI's caller does)."""
         cs = self.settings.camera_settings
-        out = np.zeros((cs.backbuffer_height, cs.backbuffer_width, 3))
+        shape = (cs.backbuffer_height, cs.backbuffer_width, 3)
+        if out is None:
+            out = np.zeros(shape)
+        elif out.shape != shape or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError(f"await_: out must be a C-contiguous float64 array of shape {shape}")
         _check(lib().rm_task_await(self._h, _ptr(out)))
         return out
 
