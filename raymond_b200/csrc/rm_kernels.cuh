@@ -630,30 +630,32 @@ __device__ __forceinline__ void lobe_f32(const RenderParams& rp, D3 normal64, D3
 // emission.  Returns true when the path continues with (o, d, T) updated; otherwise `result` is
 // the radiance the path delivers.  PREC = rm_precision: the hit point, the surface normal and the next
 // origin are f64 in both modes; the lobe sampling and the BRDF weight follow PREC.
+// What one bounce does to a path, before the path's throughput T is involved (T is read from the queue only afterwards, so
+// its six registers are free during the bounce): BOUNCE_NONE = the path ends with no radiance, BOUNCE_EMIT = it delivers
+// T (*) v, BOUNCE_CONTINUE = it goes on from (o, d) with T (*) v.
+enum Bounce : int { BOUNCE_NONE = 0, BOUNCE_EMIT = 1, BOUNCE_CONTINUE = 2 };
+
 template <int PREC>
-__device__ __forceinline__ bool shade(const DevScene& sc, const RenderParams& rp, double hit_t, int hit_obj, unsigned hit_sub, unsigned pixel,
-                                      unsigned sample, unsigned depth, D3& o, D3& d, D3& T, D3& result, unsigned& shaded_tri) {
-    result = d3(0.0, 0.0, 0.0);
-    if (hit_obj < 0) return false;                                          // :242
+__device__ __forceinline__ Bounce shade(const DevScene& sc, const RenderParams& rp, double hit_t, int hit_obj, unsigned hit_sub, unsigned pixel,
+                                        unsigned sample, unsigned depth, D3& o, D3& d, D3& v, unsigned& shaded_tri) {
+    if (hit_obj < 0) return BOUNCE_NONE;                                    // :242
     const DevObject& ob = sc.obj[hit_obj];
     const D3 frag = o + d * hit_t;                                          // :246
-    if (ob.mat == RM_MATERIAL_EMISSION) { result = mul(T, ld3(ob.color)); return false; }   // :250
-    if (depth >= rp.bounce_limit) return false;                             // the child call returns 0 (:235-237)
+    if (ob.mat == RM_MATERIAL_EMISSION) { v = ld3(ob.color); return BOUNCE_EMIT; }   // :250
+    if (depth >= rp.bounce_limit) return BOUNCE_NONE;                       // the child call returns 0 (:235-237)
     D3 normal;                                                              // :244
     if (ob.geom == GEOM_PLANE) normal = ld3(ob.g + 3);
     else if (ob.geom == GEOM_SPHERE) normal = normalize(frag - ld3(ob.g));
     else { normal = triangle_normal(sc.grid[ob.grid], hit_sub, frag); shaded_tri++; }
     const D3 to_camera = ld3(rp.cam.pos) - frag;
     const double metal = ob.mat == RM_MATERIAL_METAL ? 1.0 : 0.0;
-    D3 dir, wgt;
+    D3 dir;
     double eps;
-    if (PREC == RM_PRECISION_F32_SHADING) lobe_f32(rp, normal, to_camera, ld3(ob.color), ob.rough, metal, pixel, sample, depth, dir, wgt, eps);
-    else lobe_f64(rp, normal, to_camera, ld3(ob.color), ob.rough, metal, pixel, sample, depth, dir, wgt, eps);
-    T = mul(T, wgt);
-    if (T.x == 0.0 && T.y == 0.0 && T.z == 0.0) return false;   // nothing downstream can change a zero path value
+    if (PREC == RM_PRECISION_F32_SHADING) lobe_f32(rp, normal, to_camera, ld3(ob.color), ob.rough, metal, pixel, sample, depth, dir, v, eps);
+    else lobe_f64(rp, normal, to_camera, ld3(ob.color), ob.rough, metal, pixel, sample, depth, dir, v, eps);
     o = frag + normal * eps;
     d = dir;
-    return true;
+    return BOUNCE_CONTINUE;
 }
 
 // ===================================================================== kernels
@@ -794,6 +796,10 @@ constexpr unsigned kLook = RM_TRAV_LOOK;                  // cells looked ahead 
 constexpr unsigned kTravMaxSteps = RM_TRAV_MAX_STEPS;     // walk iterations per phase A
 constexpr unsigned kRefillMin = RM_TRAV_REFILL_MIN;       // idle lanes that trigger a re-fill while others still have work
 
+// RM_TRAV_PARK (default on): the lane's DDA state lives in shared memory between walks, see TravWarpShared::dda_t
+#ifndef RM_TRAV_PARK
+#define RM_TRAV_PARK 1
+#endif
 struct TravWarpShared {
     double2 ray[32][3];                // {o.x o.y} {o.z d.x} {d.y d.z} of the lane's ray (three 128-bit accesses)
     unsigned long long cand_t[32];     // this round's smallest distance bits per ray
@@ -805,6 +811,12 @@ struct TravWarpShared {
     unsigned char s_owner[64];         // ... and the lane that owns the ray
     double best_t[32];                 // the lane's ray: closest hit among the objects evaluated before this grid (from the
     int best_obj[32];                  // traversal record), merged with the grid's answer when the ray finishes
+#if RM_TRAV_PARK
+    double dda_t[6][32];               // t_max xyz, t_delta xyz of the lane's ray while it is not walking (phase B / C): the DDA state
+    int dda_c[3][32];                  // lives in registers only inside phase A, which lets the pooled loops run with 18 fewer
+    unsigned dda_s[32];                // live registers (current cell; bit a set: step along axis a is -1)
+    unsigned ray_index[32];            // index of the lane's ray in the stage's queue (needed once, when it finishes)
+#endif
 };
 
 enum TravState : unsigned { TS_IDLE = 0, TS_LOOK = 1, TS_STEP = 2, TS_READY = 3 };
@@ -831,10 +843,16 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
     unsigned state = TS_IDLE;
     bool exhausted = false;                 // the queue has no more records for this warp
     // DDA state of MY ray (acc_grid.rs:100-125)
+#if !RM_TRAV_PARK
     double tmx = 0, tmy = 0, tmz = 0, tdx = 0, tdy = 0, tdz = 0;
     int cx = 0, cy = 0, cz = 0, sx = 1, sy = 1, sz = 1;
+#endif
     const unsigned rx = (unsigned)g.res[0], ry = (unsigned)g.res[1], rz = (unsigned)g.res[2];
+#if RM_TRAV_PARK
+    unsigned k = 0, cnt = 0;
+#else
     unsigned ray = 0, k = 0, cnt = 0;
+#endif
     unsigned n_cells = 0, n_tests = 0, n_surv = 0, n_occ = 0, n_flops = 0;
 #if defined(RM_TRAV_PROFILE)
     unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -856,13 +874,30 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
                     const double* rec = a.trav + (size_t)idx * kTravDoubles;
                     double ox, oy, oz, dx, dy, dz, q0, q1, q2, q3;
                     ld256(rec, ox, oy, oz, dx);
+#if RM_TRAV_PARK
+                    {
+                        double t0, t1, t2, t3, t4, t5;
+                        ld256(rec + 4, dy, dz, t0, t1);
+                        ld256(rec + 8, t2, t3, t4, t5);
+                        ld256(rec + 12, q0, q1, q2, q3);
+                        sh.dda_t[0][lane] = t0; sh.dda_t[1][lane] = t1; sh.dda_t[2][lane] = t2;
+                        sh.dda_t[3][lane] = t3; sh.dda_t[4][lane] = t4; sh.dda_t[5][lane] = t5;
+                        sh.dda_c[0][lane] = __double2loint(q0); sh.dda_c[1][lane] = __double2hiint(q0); sh.dda_c[2][lane] = __double2loint(q1);
+                        sh.dda_s[lane] = (unsigned)__double2hiint(q1);
+                    }
+#else
                     ld256(rec + 4, dy, dz, tmx, tmy);
                     ld256(rec + 8, tmz, tdx, tdy, tdz);
                     ld256(rec + 12, q0, q1, q2, q3);
                     cx = __double2loint(q0); cy = __double2hiint(q0); cz = __double2loint(q1);
                     const unsigned neg = (unsigned)__double2hiint(q1);
                     sx = (neg & 1u) ? -1 : 1; sy = (neg & 2u) ? -1 : 1; sz = (neg & 4u) ? -1 : 1;
+#endif
+#if RM_TRAV_PARK
+                    sh.ray_index[lane] = (unsigned)__double2loint(q2);
+#else
                     ray = (unsigned)__double2loint(q2);
+#endif
                     sh.best_obj[lane] = __double2hiint(q2);
                     sh.best_t[lane] = q3;
                     sh.ray[lane][0] = make_double2(ox, oy);
@@ -882,6 +917,18 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
         // so each iteration looks kLook cells ahead: the DDA is advanced kLook times in registers (the arithmetic is
         // cheap and exactly the reference's sequence), the kLook occupancy words are fetched together, and the ray
         // commits up to the first occupied cell (re-walking from the saved state) or all kLook empty ones.
+#if RM_TRAV_PARK
+        double tmx = 0, tmy = 0, tmz = 0, tdx = 0, tdy = 0, tdz = 0;
+        int cx = 0, cy = 0, cz = 0, sx = 1, sy = 1, sz = 1;
+        const bool walking = state == TS_LOOK || state == TS_STEP;
+        if (walking) {
+            tmx = sh.dda_t[0][lane]; tmy = sh.dda_t[1][lane]; tmz = sh.dda_t[2][lane];
+            tdx = sh.dda_t[3][lane]; tdy = sh.dda_t[4][lane]; tdz = sh.dda_t[5][lane];
+            cx = sh.dda_c[0][lane]; cy = sh.dda_c[1][lane]; cz = sh.dda_c[2][lane];
+            const unsigned neg = sh.dda_s[lane];
+            sx = (neg & 1u) ? -1 : 1; sy = (neg & 2u) ? -1 : 1; sz = (neg & 4u) ? -1 : 1;
+        }
+#endif
 #pragma unroll 1
         for (unsigned it = 0; it < kTravMaxSteps; it++) {
             if (state == TS_LOOK) {                              // a fresh ray: its start cell, no step (acc_grid.rs:127-131)
@@ -932,6 +979,12 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
             }
             if (!__any_sync(FULL, state == TS_STEP)) break;
         }
+#if RM_TRAV_PARK
+        if (walking) {
+            sh.dda_t[0][lane] = tmx; sh.dda_t[1][lane] = tmy; sh.dda_t[2][lane] = tmz;
+            sh.dda_c[0][lane] = cx; sh.dda_c[1][lane] = cy; sh.dda_c[2][lane] = cz;
+        }
+#endif
         // the cell records of every ray that found an occupied cell, in one round trip (not one per walk iteration)
         if (state == TS_READY) {
             const uint2 cell = __ldg(&g.cells[k]);
@@ -1070,6 +1123,9 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
                 // the cell's closest hit is the grid's answer; merge with what the other objects found (the hit record of
                 // this ray as k_setup left it came in with the traversal record: no global read here)
                 if (closer(closest, a.grid_object, sh.best_t[lane], sh.best_obj[lane])) {
+#if RM_TRAV_PARK
+                    const unsigned ray = sh.ray_index[lane];
+#endif
                     a.hit.t[ray] = closest; a.hit.obj[ray] = a.grid_object; a.hit.sub[ray] = best_tri;
                 }
                 state = TS_IDLE;
@@ -1117,12 +1173,15 @@ __global__ void __launch_bounds__(kBlock, RM_SHADE_BLOCKS_PER_SM) k_shade(const 
             slot = FIRST ? i : qin.id[i];
             o = d3(qin.f[0][i], qin.f[1][i], qin.f[2][i]);
             d = d3(qin.f[3][i], qin.f[4][i], qin.f[5][i]);
-            T = FIRST ? d3(1.0, 1.0, 1.0) : d3(qin.f[6][i], qin.f[7][i], qin.f[8][i]);
             const unsigned q = slot % rp.n_pixels, s_local = slot / rp.n_pixels;
-            D3 result;
-            cont = shade<PREC>(sc, rp, hit.t[i], hit.obj[i], hit.sub[i], rp.pixel_map[q], rp.first_sample + s_local * rp.sample_stride, depth, o, d, T, result,
-                               shaded_tri);
+            D3 v = d3(0.0, 0.0, 0.0);
+            const Bounce b = shade<PREC>(sc, rp, hit.t[i], hit.obj[i], hit.sub[i], rp.pixel_map[q], rp.first_sample + s_local * rp.sample_stride, depth, o, d, v, shaded_tri);
+            // the path's value is (prod of weights) (*) emission (src/trace.rs:281-282,315-319): the throughput so far comes in only now
+            T = d3(0.0, 0.0, 0.0);
+            if (b != BOUNCE_NONE) T = mul(FIRST ? d3(1.0, 1.0, 1.0) : d3(qin.f[6][i], qin.f[7][i], qin.f[8][i]), v);
+            cont = b == BOUNCE_CONTINUE && !(T.x == 0.0 && T.y == 0.0 && T.z == 0.0);   // nothing downstream can change a zero path value
             if (!cont) {
+                const D3 result = b == BOUNCE_EMIT ? T : d3(0.0, 0.0, 0.0);
                 rp.contrib[slot] = result.x;
                 rp.contrib[(size_t)rp.cap + slot] = result.y;
                 rp.contrib[2 * (size_t)rp.cap + slot] = result.z;
