@@ -169,10 +169,19 @@ class DistributedRenderer:
         return self._host.numpy()
 
     def frame(self, sample_count: Optional[int] = None) -> Optional[np.ndarray]:
-        """The averaged frame (H, W, 3) on rank 0 (tile.data / sample_count, src/trace.rs:95), None elsewhere."""
+        """The averaged frame (H, W, 3) on rank 0 (tile.data / sample_count, src/trace.rs:95), None elsewhere.  The division
+        runs on the device on the exchanged sums (the same IEEE division) and the result lands in the pinned frame buffer of
+        this process: like sums(), the array is a view of that buffer — copy it to keep it past the next call."""
         n = self.samples_done if sample_count is None else sample_count
-        sums = self.sums()
-        return None if sums is None else sums / float(n)
+        total = self.checkpoint()
+        if total is None:
+            self.stream.synchronize()
+            return None
+        with self.torch.cuda.stream(self.stream):
+            total.div_(float(n))                   # the exchange scratch: overwritten by the next checkpoint anyway
+            self._host.copy_(total, non_blocking=True)
+        self.stream.synchronize()
+        return self._host.numpy()
 
     def render_progressive(self, on_message: Optional[Callable[[A.Message], None]] = None) -> Optional[np.ndarray]:
         """settings.sample_count samples with a checkpoint every settings.samples_per_iteration (0 = only the final one): rank 0

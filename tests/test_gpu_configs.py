@@ -42,12 +42,14 @@ def oracle_sample_frames(osc, cam, spp, seed):
     return [O.render(osc, cam, 1, seed=seed, first_sample=s, worker_count=THREADS)[0] for s in range(spp)]
 
 
-def compare_paths(gpu_frames, ora_frames, what, max_differing=0.004, max_gross=0.0015):
+def compare_paths(gpu_frames, ora_frames, what, max_differing=1e-5, max_gross=2e-6):
     """Path-for-path comparison of two same-stream renders (one frame per sample).
 
-    A path "differs" when its radiance is off by more than 1e-9 relative.  Differences come from CUDA's sincos vs glibc's
-    sin / cos / acos (<= 1 ulp) amplified by ill-conditioned steps of the reference's own arithmetic (Heron-area barycentrics
-    near a triangle edge, grazing reflections) or flipping a lobe / hit decision.  Asserted:
+    A path "differs" when its radiance is off by more than 1e-9 relative.  Measured on B200: NO path differs on either full
+    1920x1080 x 2 frame (4 147 200 paths each; largest relative difference 4e-11) — CUDA's sincos and the closed forms used
+    for cos(acos(x)) differ from glibc by <= 1 ulp, and nothing on these frames amplifies that past 1e-9.  A last-ulp
+    difference flipping a lobe / hit decision remains possible in principle, so a handful of paths are allowed, and for
+    those the magnitude and the bias are bounded too.  Asserted:
       * at most `max_differing` of the paths differ at all, at most `max_gross` by more than 1e-3 relative;
       * every differing GPU path value is finite, non-negative and no larger than twice the largest path value the oracle
         produced anywhere in these frames (it is a path the reference could have traced, not garbage);
@@ -63,7 +65,7 @@ def compare_paths(gpu_frames, ora_frames, what, max_differing=0.004, max_gross=0
     frac, gfrac = differing.mean(), gross.mean()
     bound = 2.0 * o.max()
     gd, od = g[differing], o[differing]
-    report = f"{what}: {frac:.4%} of {differing.size} paths differ (> 1e-3: {gfrac:.4%})"
+    report = f"{what}: {int(differing.sum())} of {differing.size} paths differ = {frac:.5%} (by more than 1e-3: {int(gross.sum())}; largest relative difference {rel.max():.3g})"
     print(report)
     assert frac <= max_differing, report
     assert gfrac <= max_gross, report
@@ -123,7 +125,8 @@ def test_c3_tiles_over_eight_shares():
     assert np.array_equal(frame, one)
     want, _ = O.render(oracle_scene(objs), cam, spp, seed=31, worker_count=THREADS)
     rel = np.abs(frame * spp - want).max(axis=-1) / np.maximum(np.abs(want).max(axis=-1), 1e-3 * spp)
-    assert (rel > 1e-9).mean() < 0.004
+    print(f"C3 tiles over eight shares: {int((rel > 1e-9).sum())} of {rel.size} pixels differ beyond 1e-9 relative (largest {float(rel.max()):.3g})")
+    assert (rel > 1e-9).mean() < 1e-4          # measured: none
     # tile ownership of share 3 (a rank of a multi-process job renders exactly these pixels)
     layout = A.tile_layout(st)
     assert len(layout) == 60 * 34
@@ -165,7 +168,7 @@ def test_c2_gold_dragon_full_frame_paths(dragon):
     cam, spp = F.camera(1920, 1080), 2
     g, stats = gpu_sample_frames(ps, settings(cam, spp), spp, seed=2026)
     o = oracle_sample_frames(osc, cam, spp, seed=2026)
-    compare_paths(g, o, "C2 GoldDragon 1920x1080x2", max_differing=0.01, max_gross=0.004)
+    compare_paths(g, o, "C2 GoldDragon 1920x1080x2")
     assert stats["nonfinite_samples"] == 0
 
 
@@ -215,7 +218,8 @@ def test_c5_4k_progressive(dragon):
     want_full, cnt = O.render(osc, cam, spp, seed=77, worker_count=THREADS)
     for got, want, n in ((progressed, want_half, spi), (finished, want_full, spp)):
         rel = np.abs(got - want).max(axis=-1) / np.maximum(np.abs(want).max(axis=-1), 1e-3 * n)
-        assert (rel > 1e-9).mean() < 0.01, f"{(rel > 1e-9).mean():.3%} of the 4K pixels differ after {n} samples"
+        print(f"C5 4K after {n} samples: {int((rel > 1e-9).sum())} of {rel.size} pixels differ beyond 1e-9 relative (largest {float(rel.max()):.3g})")
+        assert (rel > 1e-9).mean() < 1e-4, f"{(rel > 1e-9).mean():.3%} of the 4K pixels differ after {n} samples"       # measured: none
         gl, ol = (np.clip(got / n, 0, 10) @ LUMA).mean(), (np.clip(want / n, 0, 10) @ LUMA).mean()
         assert abs(gl - ol) <= 0.002 * ol
     assert stats["nonfinite_samples"] == cnt["nonfinite"]

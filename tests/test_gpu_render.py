@@ -2,8 +2,8 @@
 
 Both sides draw the reference's rand::random::<f64>() calls from the same counter-based stream
 (Philox4x32-10 keyed by seed; pixel, sample, depth, draw), so the comparison can be far tighter than
-north_star (b) asks for: apart from rare paths where a last-ulp libm difference (CUDA sincos vs glibc)
-flips a branch, every pixel sum agrees to ~1e-12.  The noise-floor test of SURVEY §8d (RMSE against an
+north_star (b) asks for: every pixel sum agrees to better than 1e-9 relative (measured: 3e-10 at worst; a last-ulp
+libm difference — CUDA sincos vs glibc — flipping a branch is possible in principle and has room of one pixel).  The noise-floor test of SURVEY §8d (RMSE against an
 independent-seed oracle render, mean luminance) is applied as well, with the tolerances written below."""
 import numpy as np
 import pytest
@@ -30,14 +30,17 @@ def gpu_render(objs, cam, spp, seed=0, **kw):
     return sums, stats
 
 
-def compare_same_stream(gpu_sums, ora_sums, spp, what, max_outlier_frac=0.004):
+def compare_same_stream(gpu_sums, ora_sums, spp, what, max_outlier_frac=1e-4):
     g, o = gpu_sums / spp, ora_sums / spp
     assert np.isfinite(g).all()
     diff = np.abs(g - o).max(axis=-1)
     scale = np.maximum(np.abs(o).max(axis=-1), 1e-3)
     outliers = (diff / scale) > 1e-9
     frac = outliers.mean()
-    assert frac <= max_outlier_frac, f"{what}: {frac:.4%} of pixels differ beyond 1e-9 relative (allowed {max_outlier_frac:.2%})"
+    print(f"{what}: {int(outliers.sum())} of {outliers.size} pixels differ beyond 1e-9 relative (largest {float((diff / scale).max()):.3g})")
+    # measured on B200: NO pixel differs (largest relative difference 5e-12 .. 3e-10 on every scene and size); one pixel, or
+    # 1e-4 of the frame, is left as room for a last-ulp libm difference flipping a branch on another driver
+    assert outliers.sum() <= max(1, int(max_outlier_frac * outliers.size)), f"{what}: {int(outliers.sum())} pixels ({frac:.4%}) differ beyond 1e-9 relative"
     # clamp like SURVEY §8d (linear radiance clamped to [0, 10]) so one firefly cannot dominate
     gc, oc = np.clip(g, 0, 10), np.clip(o, 0, 10)
     mean_l_g, mean_l_o = (gc @ LUMA).mean(), (oc @ LUMA).mean()
@@ -94,7 +97,7 @@ def test_gold_dragon_same_stream():
     objs, cam, spp = F.gold_dragon(F.dragon_standin(240, 60)), F.camera(160, 90), 4
     g, gs = gpu_render(objs, cam, spp, seed=5)
     o, oc = O.render(oracle_scene(objs), cam, spp, seed=5)
-    compare_same_stream(g, o, spp, "GoldDragon stand-in 160x90x4", max_outlier_frac=0.01)
+    compare_same_stream(g, o, spp, "GoldDragon stand-in 160x90x4")
     assert gs["nonfinite_samples"] == oc["nonfinite"]
 
 
@@ -117,7 +120,7 @@ def test_bounce_limits(limit):
     if limit == 0:
         assert not g.any() and not o.any()
     else:
-        compare_same_stream(g, o, spp, f"bounce_limit {limit}", max_outlier_frac=0.01)
+        compare_same_stream(g, o, spp, f"bounce_limit {limit}")
     if limit == 1:
         # only directly visible emitters contribute: ceiling pixels are exactly the emission
         assert np.array_equal(g, o)
