@@ -233,7 +233,7 @@ typedef struct rm_gpu_options {
                               * its slice of the frame from all peers, in device order) straight into the frame the caller reads.
                               * rank / world_size are then set by the library.  0 or 1 = one GPU. */
     const int32_t* device_list; /* the `device_count` CUDA ordinals to use; NULL = device, device+1, ...  An ordinal may appear more
-                              * than once (several shares of the frame rendered on one GPU: same data path — scene clone, peer
+                              * than once (several shares of the frame rendered on one GPU: same data path — scene placement, peer
                               * reduce, progressive tiles — on a box with fewer GPUs). */
     uint32_t precision;      /* rm_precision */
     uint32_t reserved;

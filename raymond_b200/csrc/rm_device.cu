@@ -1218,7 +1218,7 @@ int rm_scene_intersect(const rm_scene* scene, int device, const rm_ray* rays, si
 }
 
 /* A renderer without a scene yet: stream, pixel map, wavefront queues, accumulator on options->device.  Lets the shares of a
- * multi-device task set themselves up while the scene is still being uploaded / cloned. */
+ * multi-device task set themselves up while the scene is still being uploaded and gathered. */
 rm_renderer* rm_renderer_create_unbound(const rm_settings* settings, const rm_gpu_options* options) {
     if (!settings) { fail(RM_ERR_INVALID_ARGUMENT, "rm_renderer_create_unbound: null argument"); return nullptr; }
     rm_renderer* r = new rm_renderer();

@@ -1,7 +1,7 @@
 """Several shares of a frame driven from ONE process through the C ABI (rm_gpu_options.device_count / device_list): samples
-or tiles are split between the devices, the scene is uploaded once and cloned device to device, and the accumulators are
-combined over peer memory.  The device list may name an ordinal more than once, so the whole data path — clone, peer
-reduce, progressive tiles — runs on a 1-GPU box too; with >= 2 GPUs (gpurun --gpus 2) the same tests also use real peers."""
+or tiles are split between the devices, the scene crosses the bus once in slices (one per share) and is gathered device to
+device, and the accumulators are combined over peer memory.  The device list may name an ordinal more than once, so the whole
+data path — sliced upload + gather, peer reduce, progressive tiles — runs on a 1-GPU box too; with >= 2 GPUs (gpurun --gpus 2) the same tests also use real peers."""
 import numpy as np
 import pytest
 
