@@ -803,6 +803,9 @@ constexpr unsigned kRefillMin = RM_TRAV_REFILL_MIN;       // idle lanes that tri
 #ifndef RM_TRAV_PARK
 #define RM_TRAV_PARK 1
 #endif
+#ifndef RM_TRAV_EXCL_SHARED
+#define RM_TRAV_EXCL_SHARED 1
+#endif
 struct TravWarpShared {
     double2 ray[32][3];                // {o.x o.y} {o.z d.x} {d.y d.z} of the lane's ray (three 128-bit accesses)
     unsigned long long cand_t[32];     // this round's smallest distance bits per ray
@@ -821,6 +824,10 @@ struct TravWarpShared {
     unsigned ray_index[32];            // index of the lane's ray in the stage's queue (needed once, when it finishes)
     unsigned long long cell_t[32];     // closest hit of the lane's ray in its current cell (distance bits, triangle): touched only
     unsigned cell_tri[32];             // when a round found a hit and when the ray finishes
+    unsigned char state[32];           // the lane's TravState during the pooled phase
+#endif
+#if RM_TRAV_EXCL_SHARED
+    unsigned excl[32];                 // first pool item of the lane's list (~0: none): read by locate() every round
 #endif
 };
 
@@ -1007,13 +1014,19 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
         }
         const unsigned total = __reduce_add_sync(FULL, mine);        // warp-uniform by construction (a uniform register, not one per lane)
         if (total == 0) continue;
+#if RM_TRAV_PARK
+        sh.state[lane] = (unsigned char)state;                       // not needed until phase C
+#endif
         // The pool: items [excl, excl + mine) belong to this lane's cell.  Contributing lanes are compacted into
         // olane / odelta; a round of 32 consecutive items finds its owners with one ballot and one redux:
         //   first = contributors whose list starts at or before the round, bits = list starts inside the round
         // first item of MY list; ~0 for a lane that contributes none (neither "at or before the round" nor "inside it": the two
         // tests of locate() need no separate flag)
-        const unsigned excl = mine ? incl - mine : ~0u;
         {
+            const unsigned excl = mine ? incl - mine : ~0u;
+#if RM_TRAV_EXCL_SHARED
+            sh.excl[lane] = excl;
+#endif
             const unsigned contrib = __ballot_sync(FULL, mine != 0u);
             if (mine) {
                 const unsigned q = __popc(contrib & lt);
@@ -1021,6 +1034,9 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
                 sh.odelta[q] = k - excl;
             }
         }
+#if !RM_TRAV_EXCL_SHARED
+        const unsigned excl = mine ? incl - mine : ~0u;
+#endif
         sh.cand_t[lane] = ~0ull;
         sh.cand_tri[lane] = ~0u;
 #if RM_TRAV_PARK
@@ -1033,6 +1049,9 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
         __syncwarp();
         // (owner lane, list position) of item rbase + lane; rbase is warp-uniform and every lane takes part
         auto locate = [&](unsigned rbase, unsigned& owner, unsigned& pos) {
+#if RM_TRAV_EXCL_SHARED
+            const unsigned excl = sh.excl[lane];
+#endif
             const unsigned first = __popc(__ballot_sync(FULL, excl <= rbase)) - 1u;
             const unsigned off = excl - rbase;                                   // 1..31 when my list starts inside the round
             const unsigned bits = __reduce_or_sync(FULL, (off - 1u < 31u) ? (1u << off) : 0u);
@@ -1095,12 +1114,11 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
             const bool valid = lane < take;
             bool got = false;
             unsigned long long tb = 0;
-            unsigned c_owner = 0, c_tri = 0;
+            unsigned c_owner = 0;
+            const unsigned slot = (q_head + lane) & 63u;
             if (valid) {
-                const unsigned slot = (q_head + lane) & 63u;
                 c_owner = sh.s_owner[slot];
-                c_tri = sh.s_tri[slot];
-                const TriPos tp = load_triangle(g.tri + (size_t)c_tri * 12);
+                const TriPos tp = load_triangle(g.tri + (size_t)sh.s_tri[slot] * 12);
                 const double2 r0 = sh.ray[c_owner][0], r1 = sh.ray[c_owner][1], r2 = sh.ray[c_owner][2];
                 double t;
                 unsigned fl = 0;
@@ -1116,7 +1134,7 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
             q_count -= take;
             if (__any_sync(FULL, got)) {
                 __syncwarp();
-                if (got && sh.cand_t[c_owner] == tb) atomicMin(&sh.cand_tri[c_owner], c_tri);
+                if (got && sh.cand_t[c_owner] == tb) atomicMin(&sh.cand_tri[c_owner], sh.s_tri[slot]);   // (the ring slot is read again: hits are rare)
                 __syncwarp();
                 // strict < against the earlier rounds (they hold earlier list positions) and against 5712515.0
                 const unsigned long long ct = sh.cand_t[lane];
@@ -1133,6 +1151,9 @@ __global__ void __launch_bounds__(kTravBlock, RM_TRAV_BLOCKS_PER_SM) k_traverse(
         }
         RM_PROF_MARK(2);
         // ---- C
+#if RM_TRAV_PARK
+        state = sh.state[lane];
+#endif
         if (state == TS_READY) {
 #if RM_TRAV_PARK
             const unsigned best_tri = sh.cell_tri[lane];
