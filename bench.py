@@ -539,7 +539,8 @@ def bench_ours(args):
                     times.append(dt)
             e2e = {"value": W * H * spp * e2e_steps / sum(times) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": 1e3 * sum(times) / e2e_steps,
-                   "ms_per_step_min": 1e3 * min(times), "ms_per_step_max": 1e3 * max(times), "device_ms_last_step": float(stt["device_ms"]),
+                   "ms_per_step_min": 1e3 * min(times), "ms_per_step_max": 1e3 * max(times), "ms_steps": [round(1e3 * t, 1) for t in times][:32],
+                   "device_ms_last_step": float(stt["device_ms"]),
                    "call": "render_tiled(scene, settings).await()" + (f" with rm_gpu_options.device_count = {world} (one process drives all GPUs through the C ABI)" if world > 1 else ""),
                    "mean_radiance": float(out.mean())}
         host_barrier()
