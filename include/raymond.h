@@ -370,8 +370,10 @@ int rm_write_png(const char* path, const uint8_t* rgb8, size_t width, size_t hei
  * (no FMA, as this library is compiled), in Gop/s.  Runs a ~10 ms kernel on `device`. */
 int rm_measure_fp64_rate(int device, double* gops_out);
 
-/* The library keeps the device memory of finished renders (a stream-ordered pool per GPU) and its pinned staging blocks
- * for the next call; this returns them to the driver.  Safe to call at any time no render is in flight. */
+/* The library keeps what the next frame of the same job needs again: the wavefront queues (a private stream-ordered pool per
+ * GPU, up to 48 GiB cached), scene blocks and accumulators (up to 16 GiB), the pixel launch order per frame layout (up to
+ * 512 MiB) and pinned staging blocks.  This returns all of it to the driver.  Safe to call at any time no render is in flight.
+ * RM_TRACE=1 in the environment prints the phase timings of rm_render_tiled / the render driver on stderr. */
 int rm_release_cached_memory(void);
 
 /* Tile rectangles in the reference's queue order (column-major: y advances
