@@ -208,9 +208,8 @@ rm_task* rm_render_tiled(const rm_scene* scene, const rm_settings* settings, con
     t->options.device_list = nullptr;
     t->options.device = devices[0];
     // Scene upload happens here, before the call returns, so a bad scene or a missing GPU is reported synchronously; the
-    // device copies are the snapshot (the caller may destroy `scene`).  One host thread per share: share 0 flattens the
-    // scene and uploads it (one H2D copy) while the other shares create their stream, pixel map, queues and accumulator;
-    // then every other share pulls the scene from the first device over NVLink (device-to-device, all at once).
+    // device copies are the snapshot (the caller may destroy `scene`).  One host thread per share creates the share's
+    // stream, pixel map, queues and accumulator and then joins the placement of the scene on all devices (rm_scene_group).
     Trace trace;
     t->renderers.assign(G, nullptr);
     std::vector<int> status(G, RM_OK);
