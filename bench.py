@@ -15,7 +15,7 @@ NCCL reduce inside the timed region.  `e2e` is the same frame through the refere
 render_tiled(scene, settings).await() — at N > 1 with rm_gpu_options.device_count = N, i.e. ONE process (rank 0)
 driving the N GPUs through the C ABI, which is what a Rust caller of the FFI crate gets; the one-process-per-GPU
 variant of the same frame is reported beside it as `e2e_torchrun`.  BASELINE configs[2] and configs[4] are timed at
-the same N in `other_configs`.
+the same N in `other_configs`, configs[3] (1 M-triangle soup, primary-hit query) at N = 1.
 
 One JSON line on stdout (rank 0).
 """
@@ -66,6 +66,7 @@ def parse_args():
     p.add_argument("--no-extras", action="store_true", help="skip BASELINE configs[2] / configs[4] (other_configs)")
     p.add_argument("--c3-spp", type=int, default=1000, help="samples of the configs[2] run in other_configs (tests shrink it)")
     p.add_argument("--c5-spp", type=int, default=4096, help="samples of the configs[4] run in other_configs (tests shrink it)")
+    p.add_argument("--no-c4", action="store_true", help="skip the configs[3] leg of other_configs")
     return p.parse_args()
 
 
@@ -487,6 +488,62 @@ def bench_ours(args):
             "mean_radiance": None if f5 is None else float(f5.mean())}
         d5.close()
         del d5, f5
+
+    # ---- BASELINE configs[3] (rank 0 of an N = 1 run): the 1 M-triangle soup, 1920x1080 pixel-centre primaries through the
+    #      device-resident Scene::intersect query; C and T of the byte model counted by the instrumented kernels on the jittered
+    #      camera rays of the same frame (1 spp, 1 bounce).  Its hit indices are held bit-exact to the oracle by tests/ (1-10 M).
+    if other is not None and rank == 0 and world == 1 and not args.no_c4:
+        try:
+            tris = F.triangle_soup(1_000_000, F.SOUP_BOX_CUBIC)
+            t0 = time.perf_counter()
+            sgrid = A.AccGrid.build_from_mesh(A.Mesh.new(tris), device=local)
+            build_s = time.perf_counter() - t0
+            del tris
+            soup = A.Scene()
+            soup.push_grid(sgrid, A.Material.from_fixture(F.DRAGON_MATERIAL))
+            cs4 = A.CameraSettings.from_fixture(F.camera(1920, 1080))
+            cnt = A.Renderer(soup, A.Settings(cs4, 1, (32, 32), 1), A.GpuOptions(device=local, seed=args.seed, flags=A.FLAG_COUNT_WORK))
+            cnt.render(0, 1)
+            c4s = cnt.stage_stats()
+            cnt.close()
+            g4 = max(c4s["grid_rays"][1], 1)
+            C4, T4 = c4s["cells"][1] / g4, c4s["triangle_tests"][1] / g4
+            ds4 = A.DeviceScene(soup, local)
+            n4 = 1920 * 1080
+            rays4 = torch.empty((n4, 6), dtype=torch.float64, device=f"cuda:{local}")
+            obj4 = torch.empty(n4, dtype=torch.int64, device=f"cuda:{local}")
+            sub4 = torch.empty(n4, dtype=torch.int64, device=f"cuda:{local}")
+            t4 = torch.zeros(n4, dtype=torch.float64, device=f"cuda:{local}")
+            st4 = torch.cuda.current_stream().cuda_stream
+            A.primary_rays_device(cs4, local, rays4.data_ptr(), st4)
+            for _ in range(3):
+                ds4.intersect_device(rays4.data_ptr(), n4, obj4.data_ptr(), sub4.data_ptr(), t4.data_ptr(), st4)
+            torch.cuda.synchronize()
+            best4 = None
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ds4.intersect_device(rays4.data_ptr(), n4, obj4.data_ptr(), sub4.data_ptr(), t4.data_ptr(), st4)
+                e1.record()
+                torch.cuda.synchronize()
+                best4 = e0.elapsed_time(e1) if best4 is None else min(best4, e0.elapsed_time(e1))
+            hitf = float((obj4 >= 0).float().mean())
+            entering = g4 / n4                                  # fraction of the frame's rays that enter the grid's box
+            alg_bytes = (64.0 + 8.0 * C4 + 76.0 * T4) * entering * n4
+            hbm_peak4 = 6650.0
+            try:
+                hbm_peak4 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+            except Exception:  # noqa: BLE001
+                pass
+            other["c4_triangle_soup_1m_primary_hits"] = {
+                "triangles": 1_000_000, "rays": n4, "ms": best4, "mrays_per_s": n4 / best4 / 1e3, "hit_fraction": hitf, "device_grid_build_s": build_s,
+                "cells_per_grid_ray": C4, "tests_per_grid_ray": T4, "alg_gbs": alg_bytes / (best4 * 1e-3) / 1e9, "hbm_frac_on_alg_bytes": alg_bytes / (best4 * 1e-3) / 1e9 / hbm_peak4,
+                "what": "k_setup + k_traverse + k_export_hits of one rm_device_scene_intersect call (best of 5, CUDA events); algorithmic bytes = 64 + 8 C + 76 T per grid ray "
+                        "(SURVEY 8d); 4 M / 10 M soups and the ncu capture of this regime: profiles/r2_c4_soup_*"}
+            del ds4, soup, sgrid, rays4, obj4, sub4, t4
+        except Exception as e:  # noqa: BLE001
+            log(f"[bench] configs[3] leg failed: {e!r}")
+            other["c4_triangle_soup_1m_primary_hits"] = None
 
     # ---- end to end through the reference-facing call with host buffers: render_tiled(scene, settings).await() — scene flatten +
     #      H2D inside, D2H of the f64 frame + tile slicing + averaging inside.  N > 1: (1) one process per GPU (torchrun), every
