@@ -63,3 +63,14 @@ extern "C" {
     pub fn rm_release_cached_memory() -> c_int;
     pub fn rm_measure_fp64_rate(device: c_int, gops_out: *mut f64) -> c_int;                                // diagnostic (roofline)
 }
+
+// ---- values of the enum / flag fields (include/raymond.h, RM_ABI_VERSION 2)
+pub const RM_PARTITION_SAMPLES: u32 = 0;        // rank g renders global samples g, g+G, ...
+pub const RM_PARTITION_TILES: u32 = 1;          // tiles dealt round-robin in the reference's queue order (src/trace.rs:146-172)
+pub const RM_PRECISION_F64: u32 = 0;            // the reference's f64 arithmetic throughout
+pub const RM_PRECISION_F32_SHADING: u32 = 1;    // BRDF sampling / weights in f32; intersections, hit points, normals stay f64
+pub const RM_FLAG_KEEP_NONFINITE: u32 = 1;
+pub const RM_FLAG_STAGE_TIMING: u32 = 2;
+pub const RM_FLAG_COUNT_WORK: u32 = 4;
+pub const RM_TILE_FINISHED: u32 = 0;            // Message::TileFinished
+pub const RM_TILE_PROGRESSED: u32 = 1;          // Message::TileProgressed
